@@ -1,0 +1,155 @@
+/*
+ * sph_b200.h -- C ABI of libsph_b200.so, the sm_100a WCSPH step engine.
+ *
+ * The reference (erizmr/SPH_Taichi @ 4a701fd) is pure Python + Taichi and has NO FFI of its
+ * own: the drop-in boundary is the Python class surface ParticleSystem / SPHBase /
+ * WCSPHSolver.  This ABI sits directly underneath that surface; each
+ * entry point names the reference method(s) (file:line) whose device work it replaces.  The
+ * Python shells in sph_taichi_b200/ bind it with ctypes (see INTEGRATION.md for the binding a
+ * reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SPH_E_* code on failure; the message
+ *     is available from sph_last_error().  No C++ exceptions cross the ABI.
+ *   - all device work is enqueued asynchronously on the cudaStream_t passed as `stream`
+ *     (a `void*`; NULL = legacy default stream).  No hidden synchronisation except where
+ *     stated (sph_read_status, sph_get_timers).
+ *   - device memory is owned by the caller (PyTorch): the caller allocates one workspace of
+ *     sph_workspace_bytes() bytes and the public per-particle arrays; the context only
+ *     carves the workspace.  One context per GPU / process; not thread-safe.
+ *   - there is no CPU fallback: every entry point fails with SPH_E_CUDA if no device work
+ *     can be launched.
+ */
+#ifndef SPH_B200_H
+#define SPH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPH_OK 0
+#define SPH_E_ARG (-1)      /* bad argument / state */
+#define SPH_E_CUDA (-2)     /* CUDA runtime error */
+#define SPH_E_CAPACITY (-3) /* workspace too small / too many particles */
+#define SPH_E_NCCL (-4)
+
+#define SPH_MATERIAL_SOLID 0 /* particle_system.py:30 */
+#define SPH_MATERIAL_FLUID 1 /* particle_system.py:31 */
+
+/* device status word bits (sph_read_status) */
+#define SPH_STATUS_OUT_OF_GRID 1u /* a particle hashed outside the grid (reference: OOB write) */
+#define SPH_STATUS_BAD_POLAR 2u   /* shape matching hit a singular A */
+
+/* Scalar parameters.  All constants are folded in double on the host exactly as the
+ * reference folds them in Python scope before Taichi bakes them into kernels
+ * (particle_system.py:33-46, sph_base.py:11-21,23-68, WCSPH.py:8-16). */
+typedef struct SphParams {
+    int32_t dim;            /* must be 3 (2-D is unreachable in the reference) */
+    int32_t grid_num[3];    /* ceil(domain_size / h)                   particle_system.py:44 */
+    float h;                /* support radius = grid size = padding     particle_system.py:37,43,46 */
+    float diameter;         /* particle diameter                        particle_system.py:36 */
+    float m_V0;             /* 0.8 d^3                                  particle_system.py:38 */
+    float density0;         /*                                          sph_base.py:17-18 */
+    float stiffness;        /*                                          WCSPH.py:12-13 */
+    float exponent;         /*                                          WCSPH.py:9-10 */
+    float viscosity;        /* 0.01                                     sph_base.py:15 */
+    float surface_tension;  /* 0.01                                     WCSPH.py:15 */
+    float dt;               /*                                          WCSPH.py:16 */
+    float g[3];             /*                                          sph_base.py:13 */
+    float domain_size[3];   /* domainEnd - domainStart                  particle_system.py:22 */
+    float k_w;              /* 8 / (pi h^3)                             sph_base.py:27-35 */
+    float k_dw;             /* 6 * k_w                                  sph_base.py:50-58 */
+    float visc_eps;         /* 0.01 h^2                                 WCSPH.py:113 */
+    float clamp_hi[3];      /* domain_size - padding                    sph_base.py:155-173 */
+} SphParams;
+
+/* Public per-particle arrays in the reference's field layout (particle_system.py:102-140):
+ * 3-vectors are AoS [n][3].  Pointers are DEVICE pointers.  `solid_id` is an extra i32 array
+ * prepared by the host shell: a dense immutable id 0..n_solid-1 for solid particles (the
+ * particles of one object contiguous), -1 for fluid; may be NULL when there are no solids. */
+typedef struct SphFields {
+    int32_t *object_id;
+    float *x, *x_0, *v, *acceleration;
+    float *m_V, *m, *density, *pressure;
+    int32_t *material, *is_dynamic;
+    int32_t *color;    /* [n][3], each component must be in 0..255 */
+    int32_t *grid_ids; /* output only (particle_system.py:138) */
+    int32_t *solid_id; /* input only */
+} SphFields;
+
+/* One dynamic rigid body registered for shape matching (sph_base.py:200-260). */
+typedef struct SphRigidBody {
+    int32_t object_id;
+    int32_t solid_begin, solid_end; /* range of solid_id values owned by this body */
+} SphRigidBody;
+
+typedef struct SphCtx SphCtx;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+/* Workspace bytes needed for n_max particles, n_solid solid particles, n_bodies bodies. */
+uint64_t sph_workspace_bytes(const SphParams *params, int64_t n_max, int64_t n_solid, int32_t n_bodies);
+int sph_create(const SphParams *params, int64_t n_max, int64_t n_solid, int32_t n_bodies, int32_t device,
+               void *workspace, uint64_t workspace_bytes, SphCtx **out);
+int sph_destroy(SphCtx *ctx);
+const char *sph_last_error(const SphCtx *ctx); /* ctx may be NULL: last creation error */
+int sph_set_params(SphCtx *ctx, const SphParams *params); /* e.g. solver.dt[None] = ...; grid must not change */
+
+/* ---- state transfer: ParticleSystem fields <-> packed sorted SoA (particle_system.py:102-140, 409-418) -- */
+/* number of solid particles among the n packed ones (<= n_solid of sph_create) and whether any
+ * of them is dynamic; call before sph_pack. */
+int sph_set_solid_count(SphCtx *ctx, int64_t n_solid, int32_t has_dynamic_solids);
+int sph_pack(SphCtx *ctx, const SphFields *fields, int64_t n, void *stream);
+int sph_unpack(SphCtx *ctx, const SphFields *fields, void *stream);
+int sph_unpack_xv(SphCtx *ctx, float *x, float *v, int32_t *object_id, void *stream); /* dump(): particle_system.py:409-418 */
+int sph_upload_xv(SphCtx *ctx, const float *x, const float *v, void *stream);         /* overwrite x, v in current order */
+/* inclusive cell prefix sums, the reference's grid_particles_num after the scan (particle_system.py:374) */
+int sph_copy_grid_particles_num(SphCtx *ctx, int32_t *out_dev, void *stream);
+
+/* ---- the hot path, one entry per reference method ----------------------------------------- */
+/* ParticleSystem.initialize_particle_system: update_grid_id + prefix sum + counting_sort
+ * (particle_system.py:311-375; scan_single_buffer.py:108-146) */
+int sph_neighbor_build(SphCtx *ctx, void *stream);
+/* SPHBase.compute_static_boundary_volume (moving=0) / compute_moving_boundary_volume (moving=1)
+ * (sph_base.py:91-113) */
+int sph_boundary_volume(SphCtx *ctx, int32_t moving, void *stream);
+/* WCSPHSolver.compute_densities (WCSPH.py:33-43) */
+int sph_compute_densities(SphCtx *ctx, void *stream);
+/* WCSPHSolver.compute_non_pressure_forces (WCSPH.py:128-140) */
+int sph_compute_non_pressure_forces(SphCtx *ctx, void *stream);
+/* WCSPHSolver.compute_pressure_forces (WCSPH.py:70-85) */
+int sph_compute_pressure_forces(SphCtx *ctx, void *stream);
+/* WCSPHSolver.advect (WCSPH.py:143-149) */
+int sph_advect(SphCtx *ctx, void *stream);
+/* SPHBase.enforce_boundary_3D(particle_type) (sph_base.py:149-179) */
+int sph_enforce_boundary(SphCtx *ctx, int32_t particle_type, void *stream);
+
+/* ---- rigid bodies (sph_base.py:182-260) --------------------------------------------------- */
+int sph_set_rigid_bodies(SphCtx *ctx, const SphRigidBody *bodies, int32_t n_bodies);
+/* compute_com (sph_base.py:182-192): centre of mass of body `index` -> out_dev[3] */
+int sph_compute_com(SphCtx *ctx, int32_t body_index, float *out_dev, void *stream);
+/* compute_rigid_rest_cm (sph_base.py:87-89): store current CoM as the rest CoM */
+int sph_compute_rigid_rest_cm(SphCtx *ctx, int32_t body_index, void *stream);
+/* solve_constraints (sph_base.py:200-222): shape matching; R (row-major 3x3) -> R_out_dev (may be NULL) */
+int sph_solve_constraints(SphCtx *ctx, int32_t body_index, float *R_out_dev, void *stream);
+
+/* ---- SPHBase.step (sph_base.py:263-271) + WCSPHSolver.substep (WCSPH.py:152-156) ---------- */
+/* nsteps whole steps with the fused kernels, replayed from a CUDA graph. */
+int sph_step(SphCtx *ctx, int32_t nsteps, void *stream);
+
+/* ---- diagnostics ----------------------------------------------------------------------------- */
+int sph_read_status(SphCtx *ctx, uint32_t *status_out, void *stream); /* synchronises `stream` */
+int sph_clear_status(SphCtx *ctx, void *stream);
+int64_t sph_particle_count(const SphCtx *ctx);
+/* number of kernels launched by this context since creation (graph replays counted per node) */
+int64_t sph_launch_count(const SphCtx *ctx);
+/* per-kernel timing of ONE un-graphed step with CUDA events on `stream`; synchronises.
+ * ms[] receives up to n entries in the order of sph_timer_name(i). Returns entries written. */
+int sph_profile_step(SphCtx *ctx, float *ms, int32_t n, void *stream);
+const char *sph_timer_name(int32_t i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPH_B200_H */

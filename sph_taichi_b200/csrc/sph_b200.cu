@@ -1,0 +1,554 @@
+// sph_b200.cu -- host side of libsph_b200.so: context, workspace carving, launch sequences,
+// CUDA-graph step replay, and the extern "C" ABI declared in include/sph_b200.h.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sph_kernels.cuh"
+
+namespace {
+
+std::string g_create_error;
+
+constexpr int NUM_TIMERS = 12;
+const char *kTimerNames[NUM_TIMERS] = {"zero",  "hash",    "scan",  "bucket",    "rank_move", "boundary_volume",
+                                       "density", "force", "advect_clamp", "rigid", "unused",    "total"};
+enum { T_ZERO, T_HASH, T_SCAN, T_BUCKET, T_MOVE, T_BVOL, T_DENSITY, T_FORCE, T_ADVECT, T_RIGID, T_UNUSED, T_TOTAL };
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+struct Layout {
+    uint64_t off_state[11];  // posm, veld, x0id, misc, acc (x2), aux
+    uint64_t off_cid, off_grid_ids, off_perm;
+    uint64_t off_zero_begin, off_tile_counter, off_tile_state, off_cell_end, off_cell_fill, off_zero_end;
+    uint64_t off_solid_slot, off_status, off_bodies, off_scratch;
+    uint64_t total;
+    int n_tiles;
+};
+
+Layout make_layout(int64_t n_max, int64_t C, int64_t n_solid, int n_bodies) {
+    Layout L;
+    uint64_t o = 0;
+    auto take = [&](uint64_t bytes) { uint64_t r = o; o = align_up(o + bytes, 256); return r; };
+    uint64_t n = (uint64_t)(n_max > 0 ? n_max : 1);
+    for (int k = 0; k < 11; ++k) L.off_state[k] = take(n * sizeof(float4));
+    L.off_cid = take(n * 4);
+    L.off_grid_ids = take(n * 4);
+    L.off_perm = take(n * 4);
+    L.n_tiles = (int)((C + SCAN_TILE - 1) / SCAN_TILE);
+    // one contiguous region that a single memset clears every build
+    L.off_zero_begin = o;
+    L.off_tile_counter = take(256);
+    L.off_tile_state = take((uint64_t)L.n_tiles * 8);
+    L.off_cell_end = take((uint64_t)C * 4);
+    L.off_cell_fill = take((uint64_t)C * 4);
+    L.off_zero_end = o;
+    L.off_solid_slot = take((uint64_t)(n_solid > 0 ? n_solid : 1) * 4);
+    L.off_status = take(256);
+    L.off_bodies = take((uint64_t)(n_bodies > 0 ? n_bodies : 1) * sizeof(RigidBodyDev));
+    L.off_scratch = take(256);
+    L.total = o;
+    return L;
+}
+
+}  // namespace
+
+struct SphCtx {
+    SphParams hp;
+    DevParams P;
+    DevArrays S;
+    Layout L;
+    int device = 0;
+    int64_t n_max = 0, n_solid_cap = 0;
+    int body_cap = 0;
+    char *ws = nullptr;
+    std::vector<SphRigidBody> bodies;
+    int n_dynamic_bodies = 0;
+    bool has_dynamic_solids = true;  // conservative until pack() inspects the flags
+    std::string err;
+    int64_t launches = 0;
+    // CUDA graphs, one per ping-pong parity
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    int64_t graph_kernels[2] = {0, 0};
+    int parity = 0;
+    bool built = false;  // neighbour structure valid for current positions
+};
+
+namespace {
+
+int fail(SphCtx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                        \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail((ctx), SPH_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+    } while (0)
+
+int validate_params(const SphParams *p, std::string &why) {
+    if (!p) { why = "params is NULL"; return SPH_E_ARG; }
+    if (p->dim != 3) { why = "only dim == 3 is supported (2-D is unreachable in the reference)"; return SPH_E_ARG; }
+    for (int a = 0; a < 3; ++a)
+        if (p->grid_num[a] < 3) { why = "grid_num must be >= 3 per axis"; return SPH_E_ARG; }
+    if (!(p->h > 0.f) || !(p->density0 > 0.f)) { why = "h and density0 must be positive"; return SPH_E_ARG; }
+    int64_t C = (int64_t)p->grid_num[0] * p->grid_num[1] * p->grid_num[2];
+    if (C >= (1ll << 31)) { why = "too many grid cells for int32 indices"; return SPH_E_CAPACITY; }
+    return SPH_OK;
+}
+
+void derive_params(SphCtx *c) {
+    const SphParams &h = c->hp;
+    DevParams &P = c->P;
+    P.gx = h.grid_num[0]; P.gy = h.grid_num[1]; P.gz = h.grid_num[2];
+    P.C = P.gx * P.gy * P.gz;
+    P.h = h.h; P.h2 = h.h * h.h; P.inv_h = 1.0f / h.h; P.d2 = h.diameter * h.diameter;
+    P.m_V0 = h.m_V0; P.rho0 = h.density0; P.inv_rho0sq = 1.0f / (h.density0 * h.density0);
+    P.stiffness = h.stiffness; P.exponent = h.exponent;
+    float er = std::round(h.exponent);
+    P.exponent_int = (er == h.exponent && er >= 1.f && er <= 16.f) ? (int)er : 0;
+    P.sigma = h.surface_tension; P.d_visc = (float)(2.0 * (3 + 2) * (double)h.viscosity);
+    P.visc_eps = h.visc_eps; P.dt = h.dt;
+    P.gx_ = h.g[0]; P.gy_ = h.g[1]; P.gz_ = h.g[2];
+    P.k_w = h.k_w; P.k2_w = h.k_w * 2.0f; P.k_dw = h.k_dw; P.w0 = h.k_w;
+    {   // W(d) on the host with the same expression the device uses
+        float q = h.diameter * P.inv_h;
+        if (q <= 0.5f) { float q2 = q * q; P.w_diam = h.k_w * (6.0f * q2 * q - 6.0f * q2 + 1.0f); }
+        else { float f = 1.0f - q; if (f < 0) f = 0; P.w_diam = P.k2_w * (f * f * f); }
+    }
+    P.pad = h.h; P.hi_x = h.clamp_hi[0]; P.hi_y = h.clamp_hi[1]; P.hi_z = h.clamp_hi[2];
+}
+
+void bind_arrays(SphCtx *c) {
+    char *w = c->ws;
+    const Layout &L = c->L;
+    DevArrays &S = c->S;
+    float4 *st[11];
+    for (int k = 0; k < 11; ++k) st[k] = reinterpret_cast<float4 *>(w + L.off_state[k]);
+    int p = c->parity;
+    S.posm = st[0 + 5 * p]; S.veld = st[1 + 5 * p]; S.x0id = st[2 + 5 * p]; S.misc = st[3 + 5 * p]; S.acc = st[4 + 5 * p];
+    int q = 1 - p;
+    S.posm_n = st[0 + 5 * q]; S.veld_n = st[1 + 5 * q]; S.x0id_n = st[2 + 5 * q]; S.misc_n = st[3 + 5 * q]; S.acc_n = st[4 + 5 * q];
+    S.aux = st[10];
+    S.cid = reinterpret_cast<int32_t *>(w + L.off_cid);
+    S.grid_ids = reinterpret_cast<int32_t *>(w + L.off_grid_ids);
+    S.perm = reinterpret_cast<int32_t *>(w + L.off_perm);
+    S.tile_counter = reinterpret_cast<int32_t *>(w + L.off_tile_counter);
+    S.tile_state = reinterpret_cast<unsigned long long *>(w + L.off_tile_state);
+    S.cell_end = reinterpret_cast<int32_t *>(w + L.off_cell_end);
+    S.cell_fill = reinterpret_cast<int32_t *>(w + L.off_cell_fill);
+    S.solid_slot = reinterpret_cast<int32_t *>(w + L.off_solid_slot);
+    S.status = reinterpret_cast<uint32_t *>(w + L.off_status);
+}
+
+inline RigidBodyDev *dev_bodies(SphCtx *c) { return reinterpret_cast<RigidBodyDev *>(c->ws + c->L.off_bodies); }
+inline float *dev_scratch(SphCtx *c) { return reinterpret_cast<float *>(c->ws + c->L.off_scratch); }
+
+inline int blocks_for(int64_t n, int t) { return (int)((n + t - 1) / t); }
+
+void drop_graphs(SphCtx *c) {
+    for (int k = 0; k < 2; ++k)
+        if (c->graph[k]) { cudaGraphExecDestroy(c->graph[k]); c->graph[k] = nullptr; }
+}
+
+// ---- launch sequences -----------------------------------------------------------------
+struct StageTimer {
+    cudaEvent_t ev[NUM_TIMERS + 1];
+    int stage_of[NUM_TIMERS + 1];
+    int count = 0;
+    bool on = false;
+    cudaStream_t st = nullptr;
+    void mark(int stage) {
+        if (!on) return;
+        cudaEventCreate(&ev[count]);
+        cudaEventRecord(ev[count], st);
+        stage_of[count] = stage;
+        ++count;
+    }
+};
+
+// particle_system.py:372-375.  Kernel count returned through *kernels.
+int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels) {
+    const DevParams &P = c->P;
+    if (P.n == 0) return SPH_OK;
+    const Layout &L = c->L;
+    if (tm) tm->mark(T_ZERO);
+    CUDA_TRY(c, cudaMemsetAsync(c->ws + L.off_zero_begin, 0, L.off_zero_end - L.off_zero_begin, st));
+    if (tm) tm->mark(T_HASH);
+    k_hash_count<<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
+    if (tm) tm->mark(T_SCAN);
+    k_scan<<<L.n_tiles, SCAN_THREADS, 0, st>>>(c->S.cell_end, P.C, c->S.tile_state, c->S.tile_counter);
+    if (tm) tm->mark(T_BUCKET);
+    k_bucket<<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
+    if (tm) tm->mark(T_MOVE);
+    k_rank_move<<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
+    *kernels += 4;
+    CUDA_TRY(c, cudaGetLastError());
+    c->parity ^= 1;  // sorted state now lives in the other buffer set
+    bind_arrays(c);
+    c->built = true;
+    return SPH_OK;
+}
+
+int launch_boundary_volume(SphCtx *c, int moving, cudaStream_t st, int64_t *kernels) {
+    const DevParams &P = c->P;
+    if (P.n_solid == 0) return SPH_OK;
+    k_boundary_volume<<<blocks_for(P.n_solid, 128), 128, 0, st>>>(P, c->S, moving);
+    *kernels += 1;
+    CUDA_TRY(c, cudaGetLastError());
+    return SPH_OK;
+}
+
+int launch_rigid_solve(SphCtx *c, cudaStream_t st, int64_t *kernels) {
+    // sph_base.py:247-260: per dynamic body solve_constraints, then enforce_boundary_3D(solid)
+    for (size_t b = 0; b < c->bodies.size(); ++b) {
+        k_rigid<<<1, RIGID_THREADS, 0, st>>>(c->P, c->S, dev_bodies(c), (int)b, 2, nullptr);
+        k_enforce_boundary_solid<<<blocks_for(c->P.n_solid, 256), 256, 0, st>>>(c->P, c->S);
+        *kernels += 2;
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    return SPH_OK;
+}
+
+// One whole SPHBase.step() with the fused kernels (sph_base.py:263-271, WCSPH.py:152-156).
+int launch_step(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels) {
+    const DevParams &P = c->P;
+    if (P.n == 0) return SPH_OK;
+    int rc = launch_neighbor_build(c, st, tm, kernels);
+    if (rc) return rc;
+    if (tm) tm->mark(T_BVOL);
+    if (c->has_dynamic_solids) { rc = launch_boundary_volume(c, 1, st, kernels); if (rc) return rc; }
+    if (tm) tm->mark(T_DENSITY);
+    k_density<true><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
+    if (tm) tm->mark(T_FORCE);
+    k_force<true, true><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
+    if (tm) tm->mark(T_ADVECT);
+    k_advect<true><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
+    *kernels += 3;
+    if (tm) tm->mark(T_RIGID);
+    if (!c->bodies.empty()) { rc = launch_rigid_solve(c, st, kernels); if (rc) return rc; }
+    if (tm) tm->mark(T_TOTAL);
+    CUDA_TRY(c, cudaGetLastError());
+    c->built = false;  // positions moved
+    return SPH_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+// extern "C" ABI
+// =========================================================================================
+extern "C" {
+
+uint64_t sph_workspace_bytes(const SphParams *params, int64_t n_max, int64_t n_solid, int32_t n_bodies) {
+    std::string why;
+    if (validate_params(params, why) != SPH_OK || n_max < 0 || n_solid < 0 || n_bodies < 0) return 0;
+    int64_t C = (int64_t)params->grid_num[0] * params->grid_num[1] * params->grid_num[2];
+    return make_layout(n_max, C, n_solid, n_bodies).total;
+}
+
+int sph_create(const SphParams *params, int64_t n_max, int64_t n_solid, int32_t n_bodies, int32_t device,
+               void *workspace, uint64_t workspace_bytes, SphCtx **out) {
+    if (!out) return fail(nullptr, SPH_E_ARG, "out is NULL");
+    *out = nullptr;
+    std::string why;
+    int rc = validate_params(params, why);
+    if (rc) return fail(nullptr, rc, why);
+    if (n_max < 0 || n_max >= (1ll << 31) - 1) return fail(nullptr, SPH_E_CAPACITY, "n_max out of int32 range");
+    if (n_solid < 0 || n_bodies < 0) return fail(nullptr, SPH_E_ARG, "negative capacity");
+    if (!workspace) return fail(nullptr, SPH_E_ARG, "workspace is NULL");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(nullptr, SPH_E_ARG, "workspace must be 256-byte aligned");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SPH_E_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, SPH_E_ARG, "device index out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, SPH_E_CUDA, cudaGetErrorString(e));
+    SphCtx *c = new (std::nothrow) SphCtx();
+    if (!c) return fail(nullptr, SPH_E_CAPACITY, "out of host memory");
+    c->hp = *params;
+    c->device = device;
+    c->n_max = n_max;
+    c->n_solid_cap = n_solid;
+    c->body_cap = n_bodies;
+    int64_t C = (int64_t)params->grid_num[0] * params->grid_num[1] * params->grid_num[2];
+    c->L = make_layout(n_max, C, n_solid, n_bodies);
+    if (c->L.total > workspace_bytes) { delete c; return fail(nullptr, SPH_E_CAPACITY, "workspace too small"); }
+    c->ws = static_cast<char *>(workspace);
+    c->P = DevParams{};
+    derive_params(c);
+    c->P.n = 0;
+    c->P.n_solid = 0;
+    bind_arrays(c);
+    e = cudaMemset(c->ws + c->L.off_status, 0, 256);
+    if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); delete c; return fail(nullptr, SPH_E_CUDA, m); }
+    *out = c;
+    return SPH_OK;
+}
+
+int sph_destroy(SphCtx *ctx) {
+    if (!ctx) return SPH_OK;
+    drop_graphs(ctx);
+    delete ctx;
+    return SPH_OK;
+}
+
+const char *sph_last_error(const SphCtx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sph_set_params(SphCtx *ctx, const SphParams *params) {
+    if (!ctx) return SPH_E_ARG;
+    std::string why;
+    int rc = validate_params(params, why);
+    if (rc) return fail(ctx, rc, why);
+    for (int a = 0; a < 3; ++a)
+        if (params->grid_num[a] != ctx->hp.grid_num[a]) return fail(ctx, SPH_E_ARG, "grid_num cannot change after creation");
+    ctx->hp = *params;
+    int n = ctx->P.n, ns = ctx->P.n_solid;
+    derive_params(ctx);
+    ctx->P.n = n; ctx->P.n_solid = ns;
+    drop_graphs(ctx);
+    return SPH_OK;
+}
+
+int sph_pack(SphCtx *ctx, const SphFields *f, int64_t n, void *stream) {
+    if (!ctx || !f) return SPH_E_ARG;
+    if (n < 0 || n > ctx->n_max) return fail(ctx, SPH_E_CAPACITY, "particle count exceeds n_max");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ctx->P.n = (int32_t)n;
+    drop_graphs(ctx);
+    ctx->built = false;
+    if (n == 0) return SPH_OK;
+    k_pack<<<blocks_for(n, 256), 256, 0, st>>>(ctx->P, ctx->S, *f);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
+int sph_set_solid_count(SphCtx *ctx, int64_t n_solid, int32_t has_dynamic_solids) {
+    if (!ctx) return SPH_E_ARG;
+    if (n_solid < 0 || n_solid > ctx->n_solid_cap) return fail(ctx, SPH_E_CAPACITY, "n_solid exceeds the capacity given at creation");
+    ctx->P.n_solid = (int32_t)n_solid;
+    ctx->has_dynamic_solids = has_dynamic_solids != 0;
+    drop_graphs(ctx);
+    return SPH_OK;
+}
+
+int sph_unpack(SphCtx *ctx, const SphFields *f, void *stream) {
+    if (!ctx || !f) return SPH_E_ARG;
+    if (ctx->P.n == 0) return SPH_OK;
+    k_unpack<<<blocks_for(ctx->P.n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S, *f);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
+int sph_unpack_xv(SphCtx *ctx, float *x, float *v, int32_t *object_id, void *stream) {
+    if (!ctx || !x || !v) return SPH_E_ARG;
+    if (ctx->P.n == 0) return SPH_OK;
+    k_unpack_xv<<<blocks_for(ctx->P.n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S, x, v, object_id);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
+int sph_upload_xv(SphCtx *ctx, const float *x, const float *v, void *stream) {
+    if (!ctx || !x || !v) return SPH_E_ARG;
+    if (ctx->P.n == 0) return SPH_OK;
+    k_upload_xv<<<blocks_for(ctx->P.n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S, x, v);
+    ctx->launches += 1;
+    ctx->built = false;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
+int sph_copy_grid_particles_num(SphCtx *ctx, int32_t *out_dev, void *stream) {
+    if (!ctx || !out_dev) return SPH_E_ARG;
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_dev, ctx->S.cell_end, (size_t)ctx->P.C * 4, cudaMemcpyDeviceToDevice,
+                                  static_cast<cudaStream_t>(stream)));
+    return SPH_OK;
+}
+
+int sph_neighbor_build(SphCtx *ctx, void *stream) {
+    if (!ctx) return SPH_E_ARG;
+    return launch_neighbor_build(ctx, static_cast<cudaStream_t>(stream), nullptr, &ctx->launches);
+}
+
+#define REQUIRE_BUILT(ctx)                                                                                  \
+    if (!(ctx)) return SPH_E_ARG;                                                                           \
+    if ((ctx)->P.n == 0) return SPH_OK;                                                                     \
+    if (!(ctx)->built)                                                                                      \
+        return fail((ctx), SPH_E_ARG, "neighbour structure is stale: call sph_neighbor_build first "        \
+                                      "(the reference's kernels would read an outdated grid here)");
+
+int sph_boundary_volume(SphCtx *ctx, int32_t moving, void *stream) {
+    REQUIRE_BUILT(ctx);
+    return launch_boundary_volume(ctx, moving, static_cast<cudaStream_t>(stream), &ctx->launches);
+}
+
+int sph_compute_densities(SphCtx *ctx, void *stream) {
+    REQUIRE_BUILT(ctx);
+    k_density<false><<<blocks_for(ctx->P.n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
+int sph_compute_non_pressure_forces(SphCtx *ctx, void *stream) {
+    REQUIRE_BUILT(ctx);
+    k_force<true, false><<<blocks_for(ctx->P.n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
+int sph_compute_pressure_forces(SphCtx *ctx, void *stream) {
+    REQUIRE_BUILT(ctx);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    k_eos<<<blocks_for(ctx->P.n, 256), 256, 0, st>>>(ctx->P, ctx->S);
+    k_force<false, true><<<blocks_for(ctx->P.n, 128), 128, 0, st>>>(ctx->P, ctx->S);
+    ctx->launches += 2;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
+int sph_advect(SphCtx *ctx, void *stream) {
+    if (!ctx) return SPH_E_ARG;
+    if (ctx->P.n == 0) return SPH_OK;
+    k_advect<false><<<blocks_for(ctx->P.n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S);
+    ctx->launches += 1;
+    ctx->built = false;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
+int sph_enforce_boundary(SphCtx *ctx, int32_t particle_type, void *stream) {
+    if (!ctx) return SPH_E_ARG;
+    if (ctx->P.n == 0) return SPH_OK;
+    k_enforce_boundary<<<blocks_for(ctx->P.n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S, particle_type);
+    ctx->launches += 1;
+    ctx->built = false;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
+int sph_set_rigid_bodies(SphCtx *ctx, const SphRigidBody *bodies, int32_t n_bodies) {
+    if (!ctx || n_bodies < 0 || (n_bodies > 0 && !bodies)) return SPH_E_ARG;
+    if (n_bodies > ctx->body_cap) return fail(ctx, SPH_E_CAPACITY, "more rigid bodies than the workspace was sized for");
+    ctx->bodies.assign(bodies, bodies + n_bodies);
+    std::vector<RigidBodyDev> h(n_bodies);
+    for (int b = 0; b < n_bodies; ++b) {
+        if (bodies[b].solid_begin < 0 || bodies[b].solid_end < bodies[b].solid_begin || bodies[b].solid_end > ctx->n_solid_cap)
+            return fail(ctx, SPH_E_ARG, "rigid body solid-id range out of bounds");
+        std::memset(&h[b], 0, sizeof(RigidBodyDev));
+        h[b].object_id = bodies[b].object_id;
+        h[b].solid_begin = bodies[b].solid_begin;
+        h[b].solid_end = bodies[b].solid_end;
+        h[b].R[0] = h[b].R[4] = h[b].R[8] = 1.0f;
+    }
+    if (n_bodies) CUDA_TRY(ctx, cudaMemcpy(dev_bodies(ctx), h.data(), sizeof(RigidBodyDev) * n_bodies, cudaMemcpyHostToDevice));
+    drop_graphs(ctx);
+    return SPH_OK;
+}
+
+static int rigid_call(SphCtx *ctx, int32_t body, int mode, float *out, void *stream) {
+    if (!ctx) return SPH_E_ARG;
+    if (body < 0 || body >= (int)ctx->bodies.size()) return fail(ctx, SPH_E_ARG, "rigid body index out of range");
+    k_rigid<<<1, RIGID_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S, dev_bodies(ctx), body, mode, out);
+    ctx->launches += 1;
+    if (mode == 2) ctx->built = false;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
+int sph_compute_com(SphCtx *ctx, int32_t body, float *out_dev, void *stream) {
+    if (!out_dev) return SPH_E_ARG;
+    return rigid_call(ctx, body, 0, out_dev, stream);
+}
+int sph_compute_rigid_rest_cm(SphCtx *ctx, int32_t body, void *stream) { return rigid_call(ctx, body, 1, nullptr, stream); }
+int sph_solve_constraints(SphCtx *ctx, int32_t body, float *R_out_dev, void *stream) {
+    return rigid_call(ctx, body, 2, R_out_dev, stream);
+}
+
+int sph_step(SphCtx *ctx, int32_t nsteps, void *stream) {
+    if (!ctx || nsteps < 0) return SPH_E_ARG;
+    if (ctx->P.n == 0) return SPH_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int s = 0; s < nsteps; ++s) {
+        int par = ctx->parity;
+        if (!ctx->graph[par]) {
+            // capture one step starting from this ping-pong parity
+            cudaGraph_t g = nullptr;
+            int64_t kernels = 0;
+            CUDA_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            int rc = launch_step(ctx, st, nullptr, &kernels);
+            cudaError_t e = cudaStreamEndCapture(st, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); ctx->parity = par; bind_arrays(ctx); return rc; }
+            if (e != cudaSuccess) { ctx->parity = par; bind_arrays(ctx); return fail(ctx, SPH_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e)); }
+            e = cudaGraphInstantiate(&ctx->graph[par], g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { ctx->parity = par; bind_arrays(ctx); return fail(ctx, SPH_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
+            ctx->graph_kernels[par] = kernels;
+            // capture advanced the host-side parity exactly as a real step does; rewind and replay
+            ctx->parity = par;
+            bind_arrays(ctx);
+        }
+        CUDA_TRY(ctx, cudaGraphLaunch(ctx->graph[par], st));
+        ctx->launches += ctx->graph_kernels[par];
+        ctx->parity = par ^ 1;
+        bind_arrays(ctx);
+        ctx->built = false;
+    }
+    return SPH_OK;
+}
+
+int sph_read_status(SphCtx *ctx, uint32_t *status_out, void *stream) {
+    if (!ctx || !status_out) return SPH_E_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(ctx, cudaMemcpyAsync(status_out, ctx->S.status, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return SPH_OK;
+}
+
+int sph_clear_status(SphCtx *ctx, void *stream) {
+    if (!ctx) return SPH_E_ARG;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->S.status, 0, 4, static_cast<cudaStream_t>(stream)));
+    return SPH_OK;
+}
+
+int64_t sph_particle_count(const SphCtx *ctx) { return ctx ? ctx->P.n : 0; }
+int64_t sph_launch_count(const SphCtx *ctx) { return ctx ? ctx->launches : 0; }
+
+int sph_profile_step(SphCtx *ctx, float *ms, int32_t n, void *stream) {
+    if (!ctx || !ms || n <= 0) return SPH_E_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    StageTimer tm;
+    tm.on = true;
+    tm.st = st;
+    int rc = launch_step(ctx, st, &tm, &ctx->launches);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    float out[NUM_TIMERS];
+    for (int k = 0; k < NUM_TIMERS; ++k) out[k] = 0.f;
+    for (int k = 0; k + 1 < tm.count; ++k) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, tm.ev[k], tm.ev[k + 1]);
+        out[tm.stage_of[k]] += t;
+    }
+    if (tm.count >= 2) cudaEventElapsedTime(&out[T_TOTAL], tm.ev[0], tm.ev[tm.count - 1]);
+    for (int k = 0; k < tm.count; ++k) cudaEventDestroy(tm.ev[k]);
+    int m = n < NUM_TIMERS ? n : NUM_TIMERS;
+    for (int k = 0; k < m; ++k) ms[k] = out[k];
+    return m;
+}
+
+const char *sph_timer_name(int32_t i) { return (i >= 0 && i < NUM_TIMERS) ? kTimerNames[i] : ""; }
+
+}  // extern "C"

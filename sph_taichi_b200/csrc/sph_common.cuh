@@ -1,0 +1,133 @@
+// sph_common.cuh -- shared device-side types and math for libsph_b200 (sm_100a).
+//
+// Data layout in HBM (all arrays sorted by flattened cell id, z fastest, like the reference's
+// counting sort; particle_system.py:292-294,322-369).  Everything a pair kernel gathers per
+// neighbour is one aligned 16-byte word, so a gather is a single LDG.128/LDS.128:
+//   posm[i] = {x, y, z, m_V}                         (particle_system.py:103,107)
+//   veld[i] = {vx, vy, vz, density}                  (particle_system.py:105,109)
+//   aux[i]  = fluid: {m/rho_unclamped, p/rho^2, m, 0}   solid: {body density, 0, -1|-2, 0}
+//             (-1 static, -2 dynamic) -- per-step derived data written by the density pass
+//   x0id[i] = {x_0, y_0, z_0, object_id bits}        (particle_system.py:102,104)
+//   misc[i] = {m, pressure, flags bits, solid_id bits}
+//             flags = material | is_dynamic << 1 | color r,g,b << 8,16,24
+//   acc[i]  = {ax, ay, az, 0}                        (particle_system.py:106)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sph_b200.h"
+
+#define FLAG_FLUID 1u
+#define FLAG_DYNAMIC 2u
+
+struct DevParams {
+    int32_t n;
+    int32_t n_solid;
+    int32_t C;
+    int32_t gx, gy, gz;
+    float h, h2, inv_h, d2;
+    float m_V0, rho0, inv_rho0sq, stiffness, exponent;
+    int32_t exponent_int;  // >0: exponent is that small integer (multiply chain), else powf
+    float sigma, d_visc, visc_eps, dt;
+    float gx_, gy_, gz_;
+    float k_w, k2_w, k_dw, w0, w_diam;
+    float pad, hi_x, hi_y, hi_z;
+};
+
+struct DevArrays {
+    float4 *posm, *veld, *x0id, *misc, *acc;       // current (sorted) state
+    float4 *posm_n, *veld_n, *x0id_n, *misc_n, *acc_n;  // sort destination
+    float4 *aux;
+    int32_t *cid;       // cell id per particle in pre-sort order
+    int32_t *grid_ids;  // cell id per particle in sorted order (public grid_ids)
+    int32_t *perm;      // bucket slot -> pre-sort index
+    int32_t *cell_end;  // [C] inclusive prefix sum (public grid_particles_num)
+    int32_t *cell_fill; // [C] bucket fill counters
+    unsigned long long *tile_state;
+    int32_t *tile_counter;
+    int32_t *solid_slot;  // [n_solid] solid_id -> sorted index
+    uint32_t *status;
+};
+
+__device__ __forceinline__ int cell_of(const DevParams &P, float x, float y, float z, int &ci, int &cj, int &ck) {
+    // particle_system.py:287-294 -- true division by the f32 grid size, truncation toward zero
+    ci = (int)(x / P.h);
+    cj = (int)(y / P.h);
+    ck = (int)(z / P.h);
+    return ci * P.gy * P.gz + cj * P.gz + ck;
+}
+
+// sph_base.py:23-44
+__device__ __forceinline__ float w_cubic(const DevParams &P, float r) {
+    float q = r * P.inv_h;
+    float res;
+    if (q <= 0.5f) {
+        float q2 = q * q;
+        res = P.k_w * (6.0f * q2 * q - 6.0f * q2 + 1.0f);
+    } else {
+        float f = fmaxf(1.0f - q, 0.0f);
+        res = P.k2_w * (f * f * f);
+    }
+    return res;
+}
+
+// sph_base.py:46-68: returns s such that grad W = s * r_vec  (r = |r_vec| < h assumed)
+__device__ __forceinline__ float gradw_scale(const DevParams &P, float r) {
+    float q = r * P.inv_h;
+    float s;
+    if (q <= 0.5f) {
+        s = P.k_dw * q * (3.0f * q - 2.0f);
+    } else {
+        float f = 1.0f - q;
+        s = P.k_dw * (-f * f);
+    }
+    return (r > 1e-5f && q <= 1.0f) ? s / (r * P.h) : 0.0f;
+}
+
+__device__ __forceinline__ float tait_pressure(const DevParams &P, float rho_clamped) {
+    // WCSPH.py:76
+    float x = rho_clamped / P.rho0;
+    float pw;
+    if (P.exponent_int == 7) {
+        float x2 = x * x, x4 = x2 * x2;
+        pw = x4 * x2 * x;
+    } else if (P.exponent_int > 0) {
+        pw = 1.0f;
+        for (int e = 0; e < P.exponent_int; ++e) pw *= x;
+    } else {
+        pw = powf(x, P.exponent);
+    }
+    return P.stiffness * (pw - 1.0f);
+}
+
+// Walk the 27-cell neighbourhood in the reference's order (x offset slowest, z fastest;
+// particle_system.py:378-385).  For fixed (dx, dy) the three z-cells are contiguous in the
+// sorted arrays, so the walk is 9 contiguous index ranges.  Cells outside the grid are skipped
+// (SURVEY Q3); cell 0 is invisible exactly as in the reference (Q2) because a range always
+// starts at cell_end[max(c - 1, 0)].  fn(j, rx, ry, rz, r2, posm_j) is called for j != i, r2 < h2.
+template <typename F>
+__device__ __forceinline__ void for_all_neighbors(const DevParams &P, const float4 *__restrict__ posm,
+                                                  const int32_t *__restrict__ cell_end, int i, float xi, float yi,
+                                                  float zi, F &&fn) {
+    int ci, cj, ck;
+    cell_of(P, xi, yi, zi, ci, cj, ck);
+    int k_lo = max(ck - 1, 0), k_hi = min(ck + 1, P.gz - 1);
+    for (int dx = -1; dx <= 1; ++dx) {
+        int ni = ci + dx;
+        if (ni < 0 || ni >= P.gx) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+            int nj = cj + dy;
+            if (nj < 0 || nj >= P.gy) continue;
+            int row = (ni * P.gy + nj) * P.gz;
+            int c_lo = row + k_lo, c_hi = row + k_hi;
+            int j0 = __ldg(cell_end + max(c_lo - 1, 0));
+            int j1 = __ldg(cell_end + c_hi);
+            for (int j = j0; j < j1; ++j) {
+                float4 pj = __ldg(posm + j);
+                float rx = xi - pj.x, ry = yi - pj.y, rz = zi - pj.z;
+                float r2 = rx * rx + ry * ry + rz * rz;
+                if (r2 < P.h2 && j != i) fn(j, rx, ry, rz, r2, pj);
+            }
+        }
+    }
+}

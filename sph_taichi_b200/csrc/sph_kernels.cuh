@@ -1,0 +1,534 @@
+// sph_kernels.cuh -- device kernels of libsph_b200 (sm_100a).  See sph_common.cuh for layout.
+#pragma once
+#include "sph_common.cuh"
+
+// =====================================================================================
+// state transfer (ParticleSystem fields <-> packed SoA)
+// =====================================================================================
+__global__ void k_pack(DevParams P, DevArrays S, SphFields F) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    float m_V = F.m_V[i];
+    S.posm[i] = make_float4(F.x[3 * i], F.x[3 * i + 1], F.x[3 * i + 2], m_V);
+    S.veld[i] = make_float4(F.v[3 * i], F.v[3 * i + 1], F.v[3 * i + 2], F.density[i]);
+    S.x0id[i] = make_float4(F.x_0[3 * i], F.x_0[3 * i + 1], F.x_0[3 * i + 2], __int_as_float(F.object_id[i]));
+    uint32_t flags = (F.material[i] == SPH_MATERIAL_FLUID ? FLAG_FLUID : 0u) | (F.is_dynamic[i] ? FLAG_DYNAMIC : 0u) |
+                     ((uint32_t)(F.color[3 * i] & 255) << 8) | ((uint32_t)(F.color[3 * i + 1] & 255) << 16) |
+                     ((uint32_t)(F.color[3 * i + 2] & 255) << 24);
+    int sid = F.solid_id ? F.solid_id[i] : -1;
+    S.misc[i] = make_float4(F.m[i], F.pressure[i], __uint_as_float(flags), __int_as_float(sid));
+    S.acc[i] = make_float4(F.acceleration[3 * i], F.acceleration[3 * i + 1], F.acceleration[3 * i + 2], 0.0f);
+    S.aux[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    S.grid_ids[i] = 0;
+    if (sid >= 0) S.solid_slot[sid] = i;
+}
+
+__global__ void k_unpack(DevParams P, DevArrays S, SphFields F) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    float4 a = S.posm[i], b = S.veld[i], c = S.x0id[i], d = S.misc[i], e = S.acc[i];
+    F.x[3 * i] = a.x; F.x[3 * i + 1] = a.y; F.x[3 * i + 2] = a.z; F.m_V[i] = a.w;
+    F.v[3 * i] = b.x; F.v[3 * i + 1] = b.y; F.v[3 * i + 2] = b.z; F.density[i] = b.w;
+    F.x_0[3 * i] = c.x; F.x_0[3 * i + 1] = c.y; F.x_0[3 * i + 2] = c.z; F.object_id[i] = __float_as_int(c.w);
+    uint32_t flags = __float_as_uint(d.z);
+    F.m[i] = d.x; F.pressure[i] = d.y;
+    F.material[i] = (flags & FLAG_FLUID) ? SPH_MATERIAL_FLUID : SPH_MATERIAL_SOLID;
+    F.is_dynamic[i] = (flags & FLAG_DYNAMIC) ? 1 : 0;
+    F.color[3 * i] = (flags >> 8) & 255; F.color[3 * i + 1] = (flags >> 16) & 255; F.color[3 * i + 2] = (flags >> 24) & 255;
+    F.acceleration[3 * i] = e.x; F.acceleration[3 * i + 1] = e.y; F.acceleration[3 * i + 2] = e.z;
+    if (F.grid_ids) F.grid_ids[i] = S.grid_ids[i];
+    if (F.solid_id) F.solid_id[i] = __float_as_int(d.w);
+}
+
+__global__ void k_unpack_xv(DevParams P, DevArrays S, float *x, float *v, int32_t *object_id) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    float4 a = S.posm[i], b = S.veld[i];
+    x[3 * i] = a.x; x[3 * i + 1] = a.y; x[3 * i + 2] = a.z;
+    v[3 * i] = b.x; v[3 * i + 1] = b.y; v[3 * i + 2] = b.z;
+    if (object_id) object_id[i] = __float_as_int(S.x0id[i].w);
+}
+
+__global__ void k_upload_xv(DevParams P, DevArrays S, const float *x, const float *v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    float4 a = S.posm[i], b = S.veld[i];
+    S.posm[i] = make_float4(x[3 * i], x[3 * i + 1], x[3 * i + 2], a.w);
+    S.veld[i] = make_float4(v[3 * i], v[3 * i + 1], v[3 * i + 2], b.w);
+}
+
+// =====================================================================================
+// neighbour build: hash + histogram -> single-pass scan -> bucket -> stable rank + move
+// (particle_system.py:311-375)
+// =====================================================================================
+__global__ void k_hash_count(DevParams P, DevArrays S) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    float4 p = S.posm[i];
+    int ci, cj, ck;
+    cell_of(P, p.x, p.y, p.z, ci, cj, ck);
+    bool bad = ci < 0 || ci >= P.gx || cj < 0 || cj >= P.gy || ck < 0 || ck >= P.gz || !(p.x == p.x) || !(p.y == p.y) ||
+               !(p.z == p.z);
+    if (bad) {
+        // the reference writes out of bounds here; we flag it and park the particle in range
+        atomicOr(S.status, SPH_STATUS_OUT_OF_GRID);
+        ci = min(max(ci, 0), P.gx - 1); cj = min(max(cj, 0), P.gy - 1); ck = min(max(ck, 0), P.gz - 1);
+    }
+    int c = (ci * P.gy + cj) * P.gz + ck;
+    S.cid[i] = c;
+    atomicAdd(S.cell_end + c, 1);
+}
+
+// In-place inclusive prefix sum over the per-cell counts (the reference's
+// PrefixSumExecutor.run / scan_single_buffer.py:108-146, there a 3-level recursive scan with
+// ~7 launches).  Here: ONE launch, decoupled look-back.  Each CTA takes a tile in arrival
+// order, scans it with warp shuffles + shared memory, publishes {status, value} as one 64-bit
+// word and resolves its exclusive prefix by looking back over predecessor tiles a warp at a time.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_IPT = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_IPT;
+#define SCAN_ST_AGG 1ull
+#define SCAN_ST_PREFIX 2ull
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(int32_t *__restrict__ data, int C,
+                                                        unsigned long long *tile_state, int32_t *tile_counter) {
+    __shared__ int s_tile;
+    __shared__ int s_warp[SCAN_THREADS / 32];
+    __shared__ int s_excl;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_IPT;
+
+    int v[SCAN_IPT];
+    if (base + SCAN_IPT <= C) {
+        int4 a = *reinterpret_cast<const int4 *>(data + base);
+        int4 b = *reinterpret_cast<const int4 *>(data + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; ++k) v[k] = (base + k < C) ? data[base + k] : 0;
+    }
+#pragma unroll
+    for (int k = 1; k < SCAN_IPT; ++k) v[k] += v[k - 1];
+    const int tsum = v[SCAN_IPT - 1];
+    int incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < SCAN_THREADS / 32) ? s_warp[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        if (lane < SCAN_THREADS / 32) s_warp[lane] = wi - w;  // exclusive warp offsets
+        const int agg = __shfl_sync(0xffffffffu, wi, SCAN_THREADS / 32 - 1);
+        // ---- decoupled look-back ----
+        volatile unsigned long long *st = tile_state;
+        int excl = 0;
+        if (tile > 0) {
+            if (lane == 0) st[tile] = (SCAN_ST_AGG << 32) | (unsigned int)agg;
+            int look = tile - 1;
+            while (true) {
+                int idx = look - lane;
+                unsigned long long word = (SCAN_ST_PREFIX << 32);  // virtual tile -1: prefix 0
+                if (idx >= 0) {
+                    do { word = st[idx]; } while ((word >> 32) == 0ull);
+                }
+                unsigned int is_prefix = __ballot_sync(0xffffffffu, (word >> 32) == SCAN_ST_PREFIX);
+                int val = (int)(unsigned int)(word & 0xffffffffull);
+                int upto = is_prefix ? (__ffs(is_prefix) - 1) : 31;  // nearest tile holding a full prefix
+                int contrib = (lane <= upto) ? val : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                excl += contrib;
+                if (is_prefix) break;
+                look -= 32;
+            }
+        }
+        if (lane == 0) {
+            st[tile] = (SCAN_ST_PREFIX << 32) | (unsigned int)(excl + agg);
+            s_excl = excl;
+        }
+    }
+    __syncthreads();
+    const int off = s_excl + s_warp[warp] + (incl - tsum);
+    if (base + SCAN_IPT <= C) {
+        int4 a = make_int4(v[0] + off, v[1] + off, v[2] + off, v[3] + off);
+        int4 b = make_int4(v[4] + off, v[5] + off, v[6] + off, v[7] + off);
+        *reinterpret_cast<int4 *>(data + base) = a;
+        *reinterpret_cast<int4 *>(data + base + 4) = b;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; ++k)
+            if (base + k < C) data[base + k] = v[k] + off;
+    }
+}
+
+__global__ void k_bucket(DevParams P, DevArrays S) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    int c = S.cid[i];
+    int start = c > 0 ? S.cell_end[c - 1] : 0;
+    int slot = start + atomicAdd(S.cell_fill + c, 1);
+    S.perm[slot] = i;
+}
+
+// The atomic tickets above give an arbitrary order inside a cell (as in the reference on a
+// GPU).  Ranking every bucket entry by its pre-sort index makes the result the
+// STABLE counting sort -- the serial semantics of particle_system.py:325-330 -- so the sorted
+// arrays are bit-reproducible and identical to the oracle's.
+__global__ void k_rank_move(DevParams P, DevArrays S) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n) return;
+    int src = S.perm[t];
+    int c = S.cid[src];
+    int a = c > 0 ? S.cell_end[c - 1] : 0;
+    int b = S.cell_end[c];
+    int rank = 0;
+    for (int u = a; u < b; ++u) rank += (S.perm[u] < src) ? 1 : 0;
+    int dst = a + rank;
+    float4 misc = S.misc[src];
+    S.posm_n[dst] = S.posm[src];
+    S.veld_n[dst] = S.veld[src];
+    S.x0id_n[dst] = S.x0id[src];
+    S.misc_n[dst] = misc;
+    S.acc_n[dst] = S.acc[src];
+    S.grid_ids[dst] = c;
+    int sid = __float_as_int(misc.w);
+    if (sid >= 0) S.solid_slot[sid] = dst;
+}
+
+// =====================================================================================
+// pair kernels (v1: one thread per particle, neighbours gathered through L1)
+// =====================================================================================
+
+// Akinci boundary volumes (sph_base.py:91-113).  One thread per SOLID particle.
+__global__ void __launch_bounds__(128) k_boundary_volume(DevParams P, DevArrays S, int moving) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.n_solid) return;
+    int i = S.solid_slot[s];
+    uint32_t fl = __float_as_uint(S.misc[i].z);
+    bool dyn = (fl & FLAG_DYNAMIC) != 0;
+    if (dyn != (moving != 0)) return;
+    float4 pi = S.posm[i];
+    float delta = P.w0;
+    for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
+                      [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
+                          uint32_t fj = __float_as_uint(__ldg(&S.misc[j].z));
+                          if (!(fj & FLAG_FLUID)) delta += w_cubic(P, sqrtf(r2));
+                      });
+    // only .w changes; concurrent readers use .xyz only
+    reinterpret_cast<float *>(S.posm + i)[3] = 1.0f / delta * 3.0f;
+}
+
+// Densities (WCSPH.py:33-43).  FUSE_EOS additionally applies the clamp + Tait EOS of
+// WCSPH.py:73-76 and initialises the accelerations of non-fluid particles (WCSPH.py:130-137),
+// so the fused force pass can follow immediately.
+template <bool FUSE_EOS>
+__global__ void __launch_bounds__(128) k_density(DevParams P, DevArrays S) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    float4 pi = S.posm[i];
+    float4 mi = S.misc[i];
+    uint32_t fl = __float_as_uint(mi.z);
+    if (!(fl & FLAG_FLUID)) {
+        bool dyn = (fl & FLAG_DYNAMIC) != 0;
+        S.aux[i] = make_float4(S.veld[i].w, 0.0f, dyn ? -2.0f : -1.0f, 0.0f);
+        if (FUSE_EOS) S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    float den = 0.0f;
+    for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
+                      [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
+                          den += pj.w * w_cubic(P, sqrtf(r2));
+                      });
+    float rho = pi.w * P.w0;
+    rho += den;
+    rho *= P.rho0;
+    float vol = mi.x / rho;  // m_j / rho_j with the UNCLAMPED density (viscosity)
+    if (FUSE_EOS) {
+        float rc = fmaxf(rho, P.rho0);
+        float p = tait_pressure(P, rc);
+        reinterpret_cast<float *>(S.veld + i)[3] = rc;
+        reinterpret_cast<float *>(S.misc + i)[1] = p;
+        S.aux[i] = make_float4(vol, p / (rc * rc), mi.x, 0.0f);
+    } else {
+        reinterpret_cast<float *>(S.veld + i)[3] = rho;
+        S.aux[i] = make_float4(vol, 0.0f, mi.x, 0.0f);
+    }
+}
+
+// EOS loop of compute_pressure_forces (WCSPH.py:72-76), un-fused variant
+__global__ void k_eos(DevParams P, DevArrays S) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    uint32_t fl = __float_as_uint(S.misc[i].z);
+    if (!(fl & FLAG_FLUID)) return;
+    float rc = fmaxf(S.veld[i].w, P.rho0);
+    float p = tait_pressure(P, rc);
+    reinterpret_cast<float *>(S.veld + i)[3] = rc;
+    reinterpret_cast<float *>(S.misc + i)[1] = p;
+    reinterpret_cast<float *>(S.aux + i)[1] = p / (rc * rc);
+}
+
+// Forces.  NP: compute_non_pressure_forces (WCSPH.py:88-140); PR: the gather loop of
+// compute_pressure_forces (WCSPH.py:46-68,77-85).  NP && PR is the fused production pass.
+template <bool NP, bool PR>
+__global__ void __launch_bounds__(128) k_force(DevParams P, DevArrays S) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    float4 mi = S.misc[i];
+    uint32_t fl = __float_as_uint(mi.z);
+    if (!(fl & FLAG_FLUID)) {
+        bool dyn = (fl & FLAG_DYNAMIC) != 0;
+        if (NP && !PR) S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (PR && !NP && !dyn) S.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;  // fused: initialised by k_density<true>
+    }
+    float4 pi = S.posm[i];
+    float4 vi = S.veld[i];
+    float4 ai = S.aux[i];
+    const float dpi = ai.y;                      // p_i / rho_i^2
+    const float dpi_solid = dpi + mi.y * P.inv_rho0sq;  // + p_i / rho0^2 (Akinci mirror, WCSPH.py:59)
+    const float coh_i = P.sigma / mi.x;
+    float npx = P.gx_, npy = P.gy_, npz = P.gz_;
+    float prx = 0.f, pry = 0.f, prz = 0.f;
+    for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
+                      [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
+                          float4 aj = __ldg(S.aux + j);
+                          float r = sqrtf(r2);
+                          float gs = gradw_scale(P, r);
+                          if (aj.z > 0.0f) {  // fluid neighbour
+                              if (NP) {
+                                  float w = (r2 > P.d2) ? w_cubic(P, r) : P.w_diam;
+                                  float c = coh_i * aj.z;
+                                  npx -= c * rx * w; npy -= c * ry * w; npz -= c * rz * w;
+                                  float4 vj = __ldg(S.veld + j);
+                                  float vxy = (vi.x - vj.x) * rx + (vi.y - vj.y) * ry + (vi.z - vj.z) * rz;
+                                  float sv = P.d_visc * aj.x * vxy / (r * r + P.visc_eps) * gs;
+                                  npx += sv * rx; npy += sv * ry; npz += sv * rz;
+                              }
+                              if (PR) {
+                                  float c = -P.rho0 * pj.w * (dpi + aj.y) * gs;
+                                  prx += c * rx; pry += c * ry; prz += c * rz;
+                              }
+                          } else if (PR) {  // solid neighbour (Akinci 2012)
+                              float c = -P.rho0 * pj.w * dpi_solid * gs;
+                              float fx = c * rx, fy = c * ry, fz = c * rz;
+                              prx += fx; pry += fy; prz += fz;
+                              if (aj.z < -1.5f) {  // dynamic rigid: reaction, WCSPH.py:66-68
+                                  float *a = reinterpret_cast<float *>(S.acc + j);
+                                  atomicAdd(a + 0, -fx * P.rho0 / aj.x);
+                                  atomicAdd(a + 1, -fy * P.rho0 / aj.x);
+                                  atomicAdd(a + 2, -fz * P.rho0 / aj.x);
+                              }
+                          }
+                      });
+    if (NP && PR) {
+        S.acc[i] = make_float4(npx + prx, npy + pry, npz + prz, 0.f);
+    } else if (NP) {
+        S.acc[i] = make_float4(npx, npy, npz, 0.f);
+    } else {
+        float4 a = S.acc[i];
+        S.acc[i] = make_float4(a.x + prx, a.y + pry, a.z + prz, 0.f);
+    }
+}
+
+// =====================================================================================
+// integration and domain walls
+// =====================================================================================
+__device__ __forceinline__ void wall_clamp(const DevParams &P, float4 &p, float4 &v) {
+    // sph_base.py:118-123,149-179
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    float px = p.x, py = p.y, pz = p.z;
+    if (px > P.hi_x) { nx += 1.0f; p.x = P.hi_x; }
+    if (px <= P.pad) { nx += -1.0f; p.x = P.pad; }
+    if (py > P.hi_y) { ny += 1.0f; p.y = P.hi_y; }
+    if (py <= P.pad) { ny += -1.0f; p.y = P.pad; }
+    if (pz > P.hi_z) { nz += 1.0f; p.z = P.hi_z; }
+    if (pz <= P.pad) { nz += -1.0f; p.z = P.pad; }
+    float len = sqrtf(nx * nx + ny * ny + nz * nz);
+    if (len > 1e-6f) {
+        nx /= len; ny /= len; nz /= len;
+        float f = (1.0f + 0.5f) * (v.x * nx + v.y * ny + v.z * nz);
+        v.x -= f * nx; v.y -= f * ny; v.z -= f * nz;
+    }
+}
+
+// advect (WCSPH.py:143-149); CLAMP_FLUID fuses enforce_boundary_3D(material_fluid), which only
+// touches fluid particles and therefore commutes with the rigid-body solve in between.
+template <bool CLAMP_FLUID>
+__global__ void k_advect(DevParams P, DevArrays S) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    uint32_t fl = __float_as_uint(S.misc[i].z);
+    if (!(fl & FLAG_DYNAMIC)) return;
+    float4 p = S.posm[i], v = S.veld[i], a = S.acc[i];
+    v.x += P.dt * a.x; v.y += P.dt * a.y; v.z += P.dt * a.z;
+    p.x += P.dt * v.x; p.y += P.dt * v.y; p.z += P.dt * v.z;
+    if (CLAMP_FLUID && (fl & FLAG_FLUID)) wall_clamp(P, p, v);
+    S.posm[i] = p;
+    S.veld[i] = v;
+}
+
+__global__ void k_enforce_boundary(DevParams P, DevArrays S, int particle_type) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    uint32_t fl = __float_as_uint(S.misc[i].z);
+    int mat = (fl & FLAG_FLUID) ? SPH_MATERIAL_FLUID : SPH_MATERIAL_SOLID;
+    if (mat != particle_type || !(fl & FLAG_DYNAMIC)) return;
+    float4 p = S.posm[i], v = S.veld[i];
+    wall_clamp(P, p, v);
+    S.posm[i] = p;
+    S.veld[i] = v;
+}
+
+// enforce_boundary_3D(material_solid) restricted to the solid list (cheaper than a full sweep)
+__global__ void k_enforce_boundary_solid(DevParams P, DevArrays S) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.n_solid) return;
+    int i = S.solid_slot[s];
+    uint32_t fl = __float_as_uint(S.misc[i].z);
+    if (!(fl & FLAG_DYNAMIC)) return;
+    float4 p = S.posm[i], v = S.veld[i];
+    wall_clamp(P, p, v);
+    S.posm[i] = p;
+    S.veld[i] = v;
+}
+
+// =====================================================================================
+// rigid bodies: shape matching (sph_base.py:182-222).  One CTA per call, fixed-order tree
+// reductions (deterministic), polar decomposition in fp64 on one thread.
+// =====================================================================================
+constexpr int RIGID_THREADS = 1024;
+
+struct RigidBodyDev {
+    int32_t object_id, solid_begin, solid_end;
+    float rest_cm[3];
+    float R[9];
+};
+
+template <int NV>
+__device__ __forceinline__ void block_reduce(float (&v)[NV], float *smem /* [32 * NV] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    __syncthreads();
+    if (lane == 0)
+        for (int k = 0; k < NV; ++k) smem[warp * NV + k] = v[k];
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        float t = (lane < nw) ? smem[lane * NV + k] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        v[k] = t;  // every thread holds the total
+    }
+}
+
+__device__ void polar_rotation_f64(const double A[9], double R[9], bool &ok) {
+    double X[9];
+    for (int i = 0; i < 9; ++i) X[i] = A[i];
+    ok = true;
+    for (int it = 0; it < 100; ++it) {
+        double c[9];
+        c[0] = X[4] * X[8] - X[5] * X[7]; c[1] = X[5] * X[6] - X[3] * X[8]; c[2] = X[3] * X[7] - X[4] * X[6];
+        c[3] = X[2] * X[7] - X[1] * X[8]; c[4] = X[0] * X[8] - X[2] * X[6]; c[5] = X[1] * X[6] - X[0] * X[7];
+        c[6] = X[1] * X[5] - X[2] * X[4]; c[7] = X[2] * X[3] - X[0] * X[5]; c[8] = X[0] * X[4] - X[1] * X[3];
+        double det = X[0] * c[0] + X[1] * c[1] + X[2] * c[2];
+        if (fabs(det) < 1e-300) { ok = false; break; }
+        double nx = 0, ni = 0;
+        for (int i = 0; i < 9; ++i) { nx += X[i] * X[i]; ni += (c[i] / det) * (c[i] / det); }
+        double gamma = sqrt(sqrt(ni / nx));
+        double diff = 0;
+        for (int i = 0; i < 9; ++i) {
+            double y = 0.5 * (gamma * X[i] + (c[i] / det) / gamma);
+            diff += (y - X[i]) * (y - X[i]);
+            X[i] = y;
+        }
+        if (diff < 1e-30) break;
+    }
+    for (int i = 0; i < 9; ++i) R[i] = X[i];
+}
+
+// mode 0: compute_com -> out[3];  mode 1: store rest cm;  mode 2: solve_constraints
+__global__ void __launch_bounds__(RIGID_THREADS) k_rigid(DevParams P, DevArrays S, RigidBodyDev *bodies, int body,
+                                                          int mode, float *out) {
+    __shared__ float red[32 * 9];
+    __shared__ float s_R[9];
+    RigidBodyDev *B = bodies + body;
+    const int b0 = B->solid_begin, b1 = B->solid_end;
+    float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = b0 + threadIdx.x; s < b1; s += blockDim.x) {
+        int i = S.solid_slot[s];
+        uint32_t fl = __float_as_uint(S.misc[i].z);
+        if (!(fl & FLAG_DYNAMIC)) continue;  // compute_com counts dynamic rigid particles only (Q8)
+        float4 p = S.posm[i];
+        float mass = P.m_V0 * S.veld[i].w;
+        acc4[0] += mass * p.x; acc4[1] += mass * p.y; acc4[2] += mass * p.z; acc4[3] += mass;
+    }
+    block_reduce<4>(acc4, red);
+    const float cmx = acc4[0] / acc4[3], cmy = acc4[1] / acc4[3], cmz = acc4[2] / acc4[3];
+    if (mode == 0) {
+        if (threadIdx.x == 0) { out[0] = cmx; out[1] = cmy; out[2] = cmz; }
+        return;
+    }
+    if (mode == 1) {
+        if (threadIdx.x == 0) { B->rest_cm[0] = cmx; B->rest_cm[1] = cmy; B->rest_cm[2] = cmz; }
+        return;
+    }
+    const float r0 = B->rest_cm[0], r1 = B->rest_cm[1], r2 = B->rest_cm[2];
+    float A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = b0 + threadIdx.x; s < b1; s += blockDim.x) {
+        int i = S.solid_slot[s];
+        uint32_t fl = __float_as_uint(S.misc[i].z);
+        if (!(fl & FLAG_DYNAMIC)) continue;
+        float4 p = S.posm[i], x0 = S.x0id[i];
+        float w = P.m_V0 * S.veld[i].w;
+        float q[3] = {x0.x - r0, x0.y - r1, x0.z - r2};
+        float pp[3] = {p.x - cmx, p.y - cmy, p.z - cmz};
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) A[3 * r + c] += w * pp[r] * q[c];
+    }
+    block_reduce<9>(A, red);
+    if (threadIdx.x == 0) {
+        double Ad[9], Rd[9];
+        for (int k = 0; k < 9; ++k) Ad[k] = (double)A[k];
+        bool ok;
+        polar_rotation_f64(Ad, Rd, ok);
+        if (!ok) atomicOr(S.status, SPH_STATUS_BAD_POLAR);
+        bool all_small = true;
+        float Rf[9];
+        for (int k = 0; k < 9; ++k) { Rf[k] = (float)Rd[k]; if (!(fabsf(Rf[k]) < 1e-6f)) all_small = false; }
+        if (all_small) { for (int k = 0; k < 9; ++k) Rf[k] = (k % 4 == 0) ? 1.0f : 0.0f; }
+        for (int k = 0; k < 9; ++k) { s_R[k] = Rf[k]; B->R[k] = Rf[k]; if (out) out[k] = Rf[k]; }
+    }
+    __syncthreads();
+    for (int s = b0 + threadIdx.x; s < b1; s += blockDim.x) {
+        int i = S.solid_slot[s];
+        uint32_t fl = __float_as_uint(S.misc[i].z);
+        if (!(fl & FLAG_DYNAMIC)) continue;
+        float4 p = S.posm[i], x0 = S.x0id[i];
+        float q0 = x0.x - r0, q1 = x0.y - r1, q2 = x0.z - r2;
+        float gx = cmx + (s_R[0] * q0 + s_R[1] * q1 + s_R[2] * q2);
+        float gy = cmy + (s_R[3] * q0 + s_R[4] * q1 + s_R[5] * q2);
+        float gz = cmz + (s_R[6] * q0 + s_R[7] * q1 + s_R[8] * q2);
+        p.x += (gx - p.x) * 1.0f; p.y += (gy - p.y) * 1.0f; p.z += (gz - p.z) * 1.0f;
+        S.posm[i] = p;
+    }
+}
