@@ -83,6 +83,7 @@ typedef struct SphFields {
 typedef struct SphRigidBody {
     int32_t object_id;
     int32_t solid_begin, solid_end; /* range of solid_id values owned by this body */
+    float rest_cm[3];               /* rest centre of mass (rigid_rest_cm, sph_base.py:87-89); NaN until computed */
 } SphRigidBody;
 
 typedef struct SphCtx SphCtx;

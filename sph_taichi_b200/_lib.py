@@ -64,7 +64,8 @@ class SphFields(C.Structure):
 
 
 class SphRigidBody(C.Structure):
-    _fields_ = [("object_id", C.c_int32), ("solid_begin", C.c_int32), ("solid_end", C.c_int32)]
+    _fields_ = [("object_id", C.c_int32), ("solid_begin", C.c_int32), ("solid_end", C.c_int32),
+                ("rest_cm", C.c_float * 3)]
 
 
 _lib = None

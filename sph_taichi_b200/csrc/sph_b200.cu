@@ -26,7 +26,8 @@ struct Layout {
     uint64_t off_state[11];  // posm, veld, x0id, misc, acc (x2), aux
     uint64_t off_cid, off_grid_ids, off_perm;
     uint64_t off_zero_begin, off_tile_counter, off_tile_state, off_cell_end, off_cell_fill, off_zero_end;
-    uint64_t off_solid_slot, off_status, off_bodies, off_scratch;
+    uint64_t off_solid_slot, off_status, off_bodies, off_scratch, off_nbr_list, off_nbr_cnt;
+    int64_t npad;
     uint64_t total;
     int n_tiles;
 };
@@ -52,6 +53,9 @@ Layout make_layout(int64_t n_max, int64_t C, int64_t n_solid, int n_bodies) {
     L.off_status = take(256);
     L.off_bodies = take((uint64_t)(n_bodies > 0 ? n_bodies : 1) * sizeof(RigidBodyDev));
     L.off_scratch = take(256);
+    L.npad = (int64_t)align_up(n, 32);
+    L.off_nbr_cnt = take((uint64_t)L.npad * 4);
+    L.off_nbr_list = take((uint64_t)L.npad * 4 * NBR_CAP);
     L.total = o;
     return L;
 }
@@ -76,6 +80,7 @@ struct SphCtx {
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     int64_t graph_kernels[2] = {0, 0};
     int parity = 0;
+    cudaStream_t capture_stream = nullptr;  // graphs are captured here (the legacy stream cannot capture)
     bool built = false;  // neighbour structure valid for current positions
 };
 
@@ -146,6 +151,9 @@ void bind_arrays(SphCtx *c) {
     S.cell_fill = reinterpret_cast<int32_t *>(w + L.off_cell_fill);
     S.solid_slot = reinterpret_cast<int32_t *>(w + L.off_solid_slot);
     S.status = reinterpret_cast<uint32_t *>(w + L.off_status);
+    S.nbr_list = reinterpret_cast<int32_t *>(w + L.off_nbr_list);
+    S.nbr_cnt = reinterpret_cast<int32_t *>(w + L.off_nbr_cnt);
+    S.npad = (int32_t)L.npad;
 }
 
 inline RigidBodyDev *dev_bodies(SphCtx *c) { return reinterpret_cast<RigidBodyDev *>(c->ws + c->L.off_bodies); }
@@ -226,9 +234,9 @@ int launch_step(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels) {
     if (tm) tm->mark(T_BVOL);
     if (c->has_dynamic_solids) { rc = launch_boundary_volume(c, 1, st, kernels); if (rc) return rc; }
     if (tm) tm->mark(T_DENSITY);
-    k_density<true><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
+    k_density_list<true><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
     if (tm) tm->mark(T_FORCE);
-    k_force<true, true><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
+    k_force_list<<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
     if (tm) tm->mark(T_ADVECT);
     k_advect<true><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
     *kernels += 3;
@@ -297,6 +305,7 @@ int sph_create(const SphParams *params, int64_t n_max, int64_t n_solid, int32_t 
 int sph_destroy(SphCtx *ctx) {
     if (!ctx) return SPH_OK;
     drop_graphs(ctx);
+    if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
     delete ctx;
     return SPH_OK;
 }
@@ -451,6 +460,7 @@ int sph_set_rigid_bodies(SphCtx *ctx, const SphRigidBody *bodies, int32_t n_bodi
         h[b].object_id = bodies[b].object_id;
         h[b].solid_begin = bodies[b].solid_begin;
         h[b].solid_end = bodies[b].solid_end;
+        for (int k = 0; k < 3; ++k) h[b].rest_cm[k] = bodies[b].rest_cm[k];
         h[b].R[0] = h[b].R[4] = h[b].R[8] = 1.0f;
     }
     if (n_bodies) CUDA_TRY(ctx, cudaMemcpy(dev_bodies(ctx), h.data(), sizeof(RigidBodyDev) * n_bodies, cudaMemcpyHostToDevice));
@@ -487,9 +497,11 @@ int sph_step(SphCtx *ctx, int32_t nsteps, void *stream) {
             // capture one step starting from this ping-pong parity
             cudaGraph_t g = nullptr;
             int64_t kernels = 0;
-            CUDA_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            int rc = launch_step(ctx, st, nullptr, &kernels);
-            cudaError_t e = cudaStreamEndCapture(st, &g);
+            if (!ctx->capture_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking));
+            cudaStream_t cs = ctx->capture_stream;
+            CUDA_TRY(ctx, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+            int rc = launch_step(ctx, cs, nullptr, &kernels);
+            cudaError_t e = cudaStreamEndCapture(cs, &g);
             if (rc) { if (g) cudaGraphDestroy(g); ctx->parity = par; bind_arrays(ctx); return rc; }
             if (e != cudaSuccess) { ctx->parity = par; bind_arrays(ctx); return fail(ctx, SPH_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e)); }
             e = cudaGraphInstantiate(&ctx->graph[par], g, 0);

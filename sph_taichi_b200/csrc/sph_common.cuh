@@ -47,7 +47,31 @@ struct DevArrays {
     int32_t *tile_counter;
     int32_t *solid_slot;  // [n_solid] solid_id -> sorted index
     uint32_t *status;
+    // per-step neighbour lists, built by the density pass and re-used by the force pass:
+    // nbr_list[k * npad + i] = sorted index of the k-th neighbour of particle i (k < NBR_CAP),
+    // in the reference's visiting order; nbr_cnt[i] = count, or NBR_OVERFLOW.
+    int32_t *nbr_list;
+    int32_t *nbr_cnt;
+    int32_t npad;
 };
+
+constexpr int NBR_CAP = 64;
+constexpr int NBR_OVERFLOW = 0x7fffffff;
+
+// r = sqrt(r2) and 1/r from one MUFU.RSQ (|rel err| ~ 1e-7); exact 0 for coincident particles
+__device__ __forceinline__ void fast_norm(float r2, float &r, float &inv_r) {
+    float t = rsqrtf(r2);
+    inv_r = (r2 > 0.0f) ? t : 0.0f;
+    r = r2 * inv_r;
+}
+
+// grad W = s * r_vec, division-free variant of gradw_scale()
+__device__ __forceinline__ float gradw_scale_fast(const DevParams &P, float r, float inv_r) {
+    float q = r * P.inv_h;
+    float f = 1.0f - q;
+    float s = (q <= 0.5f) ? P.k_dw * q * (3.0f * q - 2.0f) : P.k_dw * (-f * f);
+    return (r > 1e-5f && q <= 1.0f) ? s * (inv_r * P.inv_h) : 0.0f;
+}
 
 __device__ __forceinline__ int cell_of(const DevParams &P, float x, float y, float z, int &ci, int &cj, int &ck) {
     // particle_system.py:287-294 -- true division by the f32 grid size, truncation toward zero

@@ -148,8 +148,9 @@ class Engine:
 
     def set_rigid_bodies(self, bodies):
         arr = (_lib.SphRigidBody * max(1, len(bodies)))()
-        for i, (oid, b0, b1) in enumerate(bodies):
+        for i, (oid, b0, b1, rest_cm) in enumerate(bodies):
             arr[i].object_id, arr[i].solid_begin, arr[i].solid_end = int(oid), int(b0), int(b1)
+            arr[i].rest_cm = (C.c_float * 3)(*[float(v) for v in rest_cm])
         self._check(self.lib.sph_set_rigid_bodies(self.ctx, arr, len(bodies)), "sph_set_rigid_bodies")
 
     def compute_com(self, body_index):

@@ -98,7 +98,10 @@ class ParticleSystem:
         self.grid_particles_num = Field(self, self._t["grid_particles_num"], "grid_particles_num", derived=True)
         self.grid_particles_num_temp = self.grid_particles_num  # the scan is single-buffer here
         if self.num_rigid_bodies > 0:
-            self.rigid_rest_cm = np.full((self.num_rigid_bodies + self._n_fluid_blocks, self.dim), np.nan, np.float32)
+            # the reference sizes this num_rigid_bodies + len(fluid_blocks) and indexes it by object id
+            # (particle_system.py:91-93); also cover sparse ids
+            rows = max(self.num_rigid_bodies + self._n_fluid_blocks, max(self.object_collection) + 1)
+            self.rigid_rest_cm = np.full((rows, self.dim), np.nan, np.float32)
         self.x_vis_buffer = None
         if self.GGUI:
             self.x_vis_buffer = torch.zeros((n, 3), dtype=torch.float32, device=dev)
@@ -106,9 +109,9 @@ class ParticleSystem:
 
         # ---- engine ----
         self._dt = self.cfg.get_cfg("timeStepSize") or 1e-4
-        dyn_bodies = [b for b in self.cfg.get_rigid_bodies() if b["isDynamic"]]
+        # capacity: every solid object could be registered for shape matching
         self._engine = _engine.Engine(self._make_params(), n_max=n, n_solid=self.solid_particle_num,
-                                      n_bodies=len(dyn_bodies), device=dev)
+                                      n_bodies=self.num_rigid_bodies, device=dev)
         self._fields_dirty = True   # public tensors hold data the engine has not packed yet
         self._engine_ahead = False  # engine state is newer than the public tensors
         self._gpn_stale = True
@@ -186,7 +189,8 @@ class ParticleSystem:
                     continue
                 idx = np.nonzero(oids_sorted == body_id)[0]
                 if idx.size:
-                    bodies.append((body_id, int(idx[0]), int(idx[-1]) + 1))
+                    # a re-pack must not forget the rest centre of mass computed at initialize()
+                    bodies.append((body_id, int(idx[0]), int(idx[-1]) + 1, self.rigid_rest_cm[body_id]))
         self._t["solid_id"].copy_(sid)
         self._body_index = {b[0]: i for i, b in enumerate(bodies)}
         self._engine.set_rigid_bodies(bodies)
@@ -225,8 +229,8 @@ class ParticleSystem:
         t["x_0"][sl] = pos
         t["v"][sl] = up(new_particles_velocity, np.float32).reshape(k, 3)
         t["density"][sl] = dens
-        t["m_V"][sl] = np.float32(self.m_V0)
-        t["m"][sl] = np.float32(self.m_V0) * dens
+        t["m_V"][sl] = float(np.float32(self.m_V0))
+        t["m"][sl] = dens * float(np.float32(self.m_V0))
         t["pressure"][sl] = up(new_particle_pressure, np.float32).reshape(k)
         t["material"][sl] = up(new_particles_material, np.int32).reshape(k)
         t["is_dynamic"][sl] = up(new_particles_is_dynamic, np.int32).reshape(k)
