@@ -139,6 +139,21 @@ int sph_solve_constraints(SphCtx *ctx, int32_t body_index, float *R_out_dev, voi
 /* nsteps whole steps with the fused kernels, replayed from a CUDA graph. */
 int sph_step(SphCtx *ctx, int32_t nsteps, void *stream);
 
+/* ---- x-slab sharding across the GPUs of one node (new; the reference is single-device) -------
+ * One process per GPU.  Each rank owns the cell layers [x_lo, x_hi) of the x axis and keeps
+ * `ghost_layers` (2) layers of copies of its neighbours' particles, so one exchange per step
+ * suffices: the caller (sph_taichi_b200/slab.py) sends the raw records of its boundary layers
+ * with NCCL straight out of / into the packed arrays (sph_state_offsets), appends what it
+ * received behind the local records (sph_slab_set_counts) and calls sph_slab_step, which
+ * classifies every record as owned / ghost / dropped from its position alone, sorts, reports
+ * the next send ranges in info_dev[8] = {live, sendL_begin, sendL_end, sendR_begin, sendR_end,
+ * processed, owned, status} and advances the owned particles. */
+int sph_slab_configure(SphCtx *ctx, int32_t x_lo, int32_t x_hi, int32_t ghost_layers);
+int sph_slab_set_counts(SphCtx *ctx, int64_t n_local, int64_t n_recv);
+int sph_state_offsets(SphCtx *ctx, uint64_t *out5); /* byte offsets of posm, veld, x0id, misc, acc in the workspace */
+int sph_slab_step(SphCtx *ctx, int32_t *info_dev, int32_t sort_only, void *stream);
+int sph_slab_compute(SphCtx *ctx, void *stream); /* the part of sph_slab_step after the sort */
+
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 int sph_read_status(SphCtx *ctx, uint32_t *status_out, void *stream); /* synchronises `stream` */
 int sph_clear_status(SphCtx *ctx, void *stream);

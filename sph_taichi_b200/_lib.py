@@ -24,7 +24,8 @@ ABI_SYMBOLS = [
     "sph_boundary_volume", "sph_compute_densities", "sph_compute_non_pressure_forces", "sph_compute_pressure_forces",
     "sph_advect", "sph_enforce_boundary", "sph_set_rigid_bodies", "sph_compute_com", "sph_compute_rigid_rest_cm",
     "sph_solve_constraints", "sph_step", "sph_read_status", "sph_clear_status", "sph_particle_count",
-    "sph_launch_count", "sph_profile_step", "sph_timer_name",
+    "sph_launch_count", "sph_profile_step", "sph_timer_name", "sph_slab_configure", "sph_slab_set_counts",
+    "sph_state_offsets", "sph_slab_step", "sph_slab_compute",
 ]
 
 
@@ -117,6 +118,11 @@ def load():
         "sph_launch_count": (i64, [vp]),
         "sph_profile_step": (C.c_int, [vp, C.POINTER(C.c_float), i32, vp]),
         "sph_timer_name": (C.c_char_p, [i32]),
+        "sph_slab_configure": (C.c_int, [vp, i32, i32, i32]),
+        "sph_slab_set_counts": (C.c_int, [vp, i64, i64]),
+        "sph_state_offsets": (C.c_int, [vp, C.POINTER(u64)]),
+        "sph_slab_step": (C.c_int, [vp, vp, i32, vp]),
+        "sph_slab_compute": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -41,13 +41,13 @@ Layout make_layout(int64_t n_max, int64_t C, int64_t n_solid, int n_bodies) {
     L.off_cid = take(n * 4);
     L.off_grid_ids = take(n * 4);
     L.off_perm = take(n * 4);
-    L.n_tiles = (int)((C + SCAN_TILE - 1) / SCAN_TILE);
+    L.n_tiles = (int)((C + 1 + SCAN_TILE - 1) / SCAN_TILE);  // +1: the slab-mode trash bucket
     // one contiguous region that a single memset clears every build
     L.off_zero_begin = o;
     L.off_tile_counter = take(256);
     L.off_tile_state = take((uint64_t)L.n_tiles * 8);
-    L.off_cell_end = take((uint64_t)C * 4);
-    L.off_cell_fill = take((uint64_t)C * 4);
+    L.off_cell_end = take((uint64_t)(C + 1) * 4);
+    L.off_cell_fill = take((uint64_t)(C + 1) * 4);
     L.off_zero_end = o;
     L.off_solid_slot = take((uint64_t)(n_solid > 0 ? n_solid : 1) * 4);
     L.off_status = take(256);
@@ -192,7 +192,7 @@ int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *k
     if (tm) tm->mark(T_HASH);
     k_hash_count<<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
     if (tm) tm->mark(T_SCAN);
-    k_scan<<<L.n_tiles, SCAN_THREADS, 0, st>>>(c->S.cell_end, P.C, c->S.tile_state, c->S.tile_counter);
+    k_scan<<<L.n_tiles, SCAN_THREADS, 0, st>>>(c->S.cell_end, P.C + 1, c->S.tile_state, c->S.tile_counter);
     if (tm) tm->mark(T_BUCKET);
     k_bucket<<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
     if (tm) tm->mark(T_MOVE);
@@ -518,6 +518,70 @@ int sph_step(SphCtx *ctx, int32_t nsteps, void *stream) {
         bind_arrays(ctx);
         ctx->built = false;
     }
+    return SPH_OK;
+}
+
+int sph_slab_configure(SphCtx *ctx, int32_t x_lo, int32_t x_hi, int32_t ghost_layers) {
+    if (!ctx) return SPH_E_ARG;
+    if (x_lo < 0 || x_hi > ctx->P.gx || ghost_layers < 1 || x_hi - x_lo < ghost_layers + 1)
+        return fail(ctx, SPH_E_ARG, "slab must lie inside the grid and be at least ghost_layers + 1 cell layers wide");
+    if (!ctx->bodies.empty() || ctx->P.n_solid > 0)
+        return fail(ctx, SPH_E_ARG, "x-slab sharding supports fluid-only scenes (rigid bodies are single-GPU, SURVEY 8e)");
+    ctx->P.slab_on = 1; ctx->P.sx0 = x_lo; ctx->P.sx1 = x_hi; ctx->P.sgw = ghost_layers;
+    ctx->P.n_local = ctx->P.n;
+    drop_graphs(ctx);
+    return SPH_OK;
+}
+
+int sph_slab_set_counts(SphCtx *ctx, int64_t n_local, int64_t n_recv) {
+    if (!ctx || !ctx->P.slab_on || n_local < 0 || n_recv < 0) return SPH_E_ARG;
+    if (n_local + n_recv > ctx->n_max) return fail(ctx, SPH_E_CAPACITY, "slab: local + received particles exceed n_max");
+    ctx->P.n_local = (int32_t)n_local;
+    ctx->P.n = (int32_t)(n_local + n_recv);
+    return SPH_OK;
+}
+
+int sph_state_offsets(SphCtx *ctx, uint64_t *out5) {
+    if (!ctx || !out5) return SPH_E_ARG;
+    const float4 *cur[5] = {ctx->S.posm, ctx->S.veld, ctx->S.x0id, ctx->S.misc, ctx->S.acc};
+    for (int k = 0; k < 5; ++k) out5[k] = (uint64_t)(reinterpret_cast<const char *>(cur[k]) - ctx->ws);
+    return SPH_OK;
+}
+
+int sph_slab_compute(SphCtx *ctx, void *stream);
+
+// One sharded step: classify + sort (received records are already in place behind the local
+// ones), write the next send ranges to info_dev[8], then density / forces / integration of the
+// owned particles.  sort_only = 1 stops after the sort (initialisation).
+int sph_slab_step(SphCtx *ctx, int32_t *info_dev, int32_t sort_only, void *stream) {
+    if (!ctx || !info_dev) return SPH_E_ARG;
+    if (!ctx->P.slab_on) return fail(ctx, SPH_E_ARG, "sph_slab_configure was not called");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const DevParams &P = ctx->P;
+    if (P.n == 0) { CUDA_TRY(ctx, cudaMemsetAsync(info_dev, 0, 32, st)); return SPH_OK; }
+    int rc = launch_neighbor_build(ctx, st, nullptr, &ctx->launches);
+    if (rc) return rc;
+    k_slab_info<<<1, 32, 0, st>>>(P, ctx->S, info_dev);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (!sort_only) return sph_slab_compute(ctx, stream);
+    return SPH_OK;
+}
+
+// density / forces / integration of the owned particles after sph_slab_step(sort_only = 1)
+int sph_slab_compute(SphCtx *ctx, void *stream) {
+    if (!ctx) return SPH_E_ARG;
+    if (!ctx->P.slab_on) return fail(ctx, SPH_E_ARG, "sph_slab_configure was not called");
+    const DevParams &P = ctx->P;
+    if (P.n == 0) return SPH_OK;
+    if (!ctx->built) return fail(ctx, SPH_E_ARG, "sph_slab_compute needs a fresh sph_slab_step(sort_only = 1)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    k_density_list<true><<<blocks_for(P.n, 128), 128, 0, st>>>(P, ctx->S);
+    k_force_list<<<blocks_for(P.n, 128), 128, 0, st>>>(P, ctx->S);
+    k_advect<true><<<blocks_for(P.n, 256), 256, 0, st>>>(P, ctx->S);
+    ctx->launches += 3;
+    ctx->built = false;
+    CUDA_TRY(ctx, cudaGetLastError());
     return SPH_OK;
 }
 

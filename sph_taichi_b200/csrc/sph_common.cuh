@@ -19,6 +19,7 @@
 
 #define FLAG_FLUID 1u
 #define FLAG_DYNAMIC 2u
+#define FLAG_GHOST 4u  // x-slab sharding: copy of a neighbour rank's particle, never integrated
 
 struct DevParams {
     int32_t n;
@@ -32,6 +33,9 @@ struct DevParams {
     float gx_, gy_, gz_;
     float k_w, k2_w, k_dw, w0, w_diam;
     float pad, hi_x, hi_y, hi_z;
+    // x-slab sharding (multi-GPU): this rank owns cell layers [sx0, sx1) and keeps sgw ghost
+    // layers per side.  Records [n_local, n) were just received from the neighbour ranks.
+    int32_t slab_on, sx0, sx1, sgw, n_local;
 };
 
 struct DevArrays {

@@ -75,8 +75,48 @@ __global__ void k_hash_count(DevParams P, DevArrays S) {
         ci = min(max(ci, 0), P.gx - 1); cj = min(max(cj, 0), P.gy - 1); ck = min(max(ck, 0), P.gz - 1);
     }
     int c = (ci * P.gy + cj) * P.gz + ck;
+    if (P.slab_on) {
+        // Ownership is a pure function of the (bitwise identical) position on both ranks, so a
+        // particle is owned by exactly one rank.  Everything that is neither owned nor inside
+        // the ghost band goes to the trash bucket C, which sorts to the end.
+        float4 m = S.misc[i];
+        uint32_t fl = __float_as_uint(m.z);
+        bool received = i >= P.n_local;
+        bool in_slab = ci >= P.sx0 && ci < P.sx1;
+        bool in_band = ci >= P.sx0 - P.sgw && ci < P.sx1 + P.sgw;
+        bool was_ghost = (fl & FLAG_GHOST) != 0;
+        if (was_ghost) {
+            c = P.C;  // last step's ghosts (local) or a neighbour's ghost (received): drop
+        } else if (in_slab) {
+            // stays / becomes owned
+        } else if (received && in_band) {
+            reinterpret_cast<float *>(S.misc + i)[2] = __uint_as_float(fl | FLAG_GHOST);
+        } else {
+            c = P.C;  // left my slab (the neighbour adopts it) or outside the band
+        }
+    }
     S.cid[i] = c;
     atomicAdd(S.cell_end + c, 1);
+}
+
+// After the sort: live count and the index ranges of the boundary layers this rank must send
+// next step (layers [sx0, sx0+sgw+1) to the left neighbour, [sx1-sgw-1, sx1) to the right one).
+__global__ void k_slab_info(DevParams P, DevArrays S, int32_t *info) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int layer = P.gy * P.gz;
+    auto start_of_layer = [&](int L) {
+        L = min(max(L, 0), P.gx);
+        int c = L * layer;
+        return c > 0 ? S.cell_end[c - 1] : 0;
+    };
+    info[0] = S.cell_end[P.C - 1];                      // live particles (owned + ghosts)
+    info[1] = start_of_layer(P.sx0);                    // left send range
+    info[2] = start_of_layer(min(P.sx0 + P.sgw + 1, P.sx1));
+    info[3] = start_of_layer(max(P.sx1 - P.sgw - 1, P.sx0));  // right send range
+    info[4] = start_of_layer(P.sx1);
+    info[5] = P.n;                                      // records processed (live + trash)
+    info[6] = info[4] - info[1];                        // owned particles
+    info[7] = (int32_t)(*S.status);
 }
 
 // In-place inclusive prefix sum over the per-cell counts (the reference's
@@ -193,9 +233,12 @@ __global__ void k_rank_move(DevParams P, DevArrays S) {
     int c = S.cid[src];
     int a = c > 0 ? S.cell_end[c - 1] : 0;
     int b = S.cell_end[c];
-    int rank = 0;
-    for (int u = a; u < b; ++u) rank += (S.perm[u] < src) ? 1 : 0;
-    int dst = a + rank;
+    int dst = t;  // trash bucket (slab mode): order is irrelevant and the bucket can be huge
+    if (c < P.C) {
+        int rank = 0;
+        for (int u = a; u < b; ++u) rank += (S.perm[u] < src) ? 1 : 0;
+        dst = a + rank;
+    }
     float4 misc = S.misc[src];
     S.posm_n[dst] = S.posm[src];
     S.veld_n[dst] = S.veld[src];
@@ -371,7 +414,8 @@ __global__ void k_advect(DevParams P, DevArrays S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     uint32_t fl = __float_as_uint(S.misc[i].z);
-    if (!(fl & FLAG_DYNAMIC)) return;
+    if (!(fl & FLAG_DYNAMIC) || (fl & FLAG_GHOST)) return;
+    if (P.slab_on && S.grid_ids[i] >= P.C) return;
     float4 p = S.posm[i], v = S.veld[i], a = S.acc[i];
     v.x += P.dt * a.x; v.y += P.dt * a.y; v.z += P.dt * a.z;
     p.x += P.dt * v.x; p.y += P.dt * v.y; p.z += P.dt * v.z;
@@ -550,6 +594,7 @@ template <bool FUSE_EOS>
 __global__ void __launch_bounds__(128) k_density_list(DevParams P, DevArrays S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
+    if (P.slab_on && S.grid_ids[i] >= P.C) return;  // trash bucket
     float4 pi = S.posm[i];
     float4 mi = S.misc[i];
     uint32_t fl = __float_as_uint(mi.z);
@@ -667,9 +712,11 @@ __device__ __forceinline__ void force_pair(const DevParams &P, const DevArrays &
 __global__ void __launch_bounds__(128) k_force_list(DevParams P, DevArrays S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
+    if (P.slab_on && S.grid_ids[i] >= P.C) return;
     float4 mi = S.misc[i];
     uint32_t fl = __float_as_uint(mi.z);
     if (!(fl & FLAG_FLUID)) return;  // initialised by k_density_list<true>
+    if (fl & FLAG_GHOST) return;     // ghosts are neighbours only
     float4 pi = S.posm[i];
     float4 vi = S.veld[i];
     float4 ai = S.aux[i];

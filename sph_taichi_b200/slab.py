@@ -1,0 +1,344 @@
+"""x-slab sharding of one WCSPH scene across the GPUs of a node (one process per GPU).
+
+The reference is single-device; this is the multi-GPU extension BASELINE.json asks for
+(SURVEY.md section 8e).  Design:
+
+* The grid is cut into slabs of whole x cell-layers, balanced by particle count (``plan_slabs``).
+  After the counting sort (x-major flattening, reference ``particle_system.py:292-294``) every
+  cell layer is ONE contiguous index range of the packed arrays.
+* Interaction radius = one cell, so each rank keeps 2 ghost layers per side: densities of the
+  first ghost layer are recomputed locally from the second, and a SINGLE exchange per step is
+  enough.  A step is
+
+      exchange   : NCCL send/recv (one batched group) of the raw records of my outermost
+                   3 layers per side, straight out of / into the engine's packed arrays;
+      classify   : every record becomes owned / ghost / dropped from its position alone
+                   (``k_hash_count`` slab branch) -- migration needs no extra message;
+      sort, density (owned + ghosts), forces + integration (owned only).
+
+* The send ranges for step s+1 are known right after the sort of step s; they are all-gathered
+  while the pair kernels of step s run, so the host never waits on the device mid-step.
+
+The protocol (``SlabSimulation``) talks to a *backend* object; the CUDA engine backend is
+``EngineBackend``.  tests/test_slab_gloo.py drives the same protocol with a CPU backend over the
+gloo process group.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+GHOST_LAYERS = 2
+RECORD_ARRAYS = 4  # posm, veld, x0id, misc (acc is recomputed every step and not exchanged)
+
+
+def plan_slabs(layer_counts, world, min_width=GHOST_LAYERS + 1):
+    """Cut ``len(layer_counts)`` x cell-layers into ``world`` contiguous slabs with balanced
+    particle counts; every slab at least ``min_width`` layers wide.  Returns [(lo, hi)] * world."""
+    counts = np.asarray(layer_counts, dtype=np.int64)
+    gx = len(counts)
+    if gx < world * min_width:
+        raise ValueError(f"{gx} cell layers cannot host {world} slabs of >= {min_width} layers")
+    cum = np.concatenate([[0], np.cumsum(counts)])
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        c = int(np.searchsorted(cum, target, side="left"))
+        # keep room for the slabs on both sides
+        c = max(c, cuts[-1] + min_width)
+        c = min(c, gx - (world - r) * min_width)
+        cuts.append(c)
+    cuts.append(gx)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def layer_of(x, h):
+    """Cell layer of positions (float32 true division, truncation; particle_system.py:287-289)."""
+    return (np.asarray(x, dtype=np.float32)[:, 0] / np.float32(h)).astype(np.int32)
+
+
+class EngineBackend:
+    """CUDA engine behind the slab protocol."""
+
+    def __init__(self, cfg, n_max, device):
+        from . import engine as _engine
+        self.cfg = cfg
+        self.device = torch.device(device)
+        ds = np.array(cfg.get_cfg("domainEnd"), dtype=np.float64) - np.array(cfg.get_cfg("domainStart"))
+        radius = cfg.get_cfg("particleRadius")
+        self.h = radius * 4.0
+        self.grid_num = np.ceil(ds / self.h).astype(int)
+        params = _engine.make_params(3, self.grid_num, radius, cfg.get_cfg("density0"), cfg.get_cfg("stiffness"),
+                                     cfg.get_cfg("exponent"), cfg.get_cfg("timeStepSize"), cfg.get_cfg("gravitation"), ds)
+        self.m_V0 = float(np.float32(0.8 * (2 * radius) ** 3))
+        self.n_max = int(n_max)
+        self.eng = _engine.Engine(params, n_max=self.n_max, n_solid=0, n_bodies=0, device=self.device)
+        self.info_dev = torch.zeros(8, dtype=torch.int32, device=self.device)
+        self._floats = self.eng.workspace.view(torch.uint8)
+
+    def load(self, arrays):
+        """Pack this rank's initial particles (numpy arrays in the reference's field layout)."""
+        n = arrays["x"].shape[0]
+        dev = self.device
+
+        def t(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+
+        dens = t(arrays["density"], np.float32)
+        f = {
+            "object_id": t(arrays["object_id"], np.int32), "x": t(arrays["x"], np.float32),
+            "x_0": t(arrays["x"], np.float32), "v": t(arrays["v"], np.float32),
+            "acceleration": torch.zeros((n, 3), dtype=torch.float32, device=dev),
+            "m_V": torch.full((n,), self.m_V0, dtype=torch.float32, device=dev), "m": dens * self.m_V0,
+            "density": dens, "pressure": t(arrays["pressure"], np.float32), "material": t(arrays["material"], np.int32),
+            "is_dynamic": t(arrays["is_dynamic"], np.int32), "color": t(arrays["color"], np.int32),
+            "grid_ids": None, "solid_id": None,
+        }
+        if int((f["material"] != 1).sum().item()) != 0:
+            raise NotImplementedError("x-slab sharding supports fluid-only scenes (SURVEY.md section 8e)")
+        self.eng.pack(f, n, 0, False)
+        self._keep = f
+        torch.cuda.synchronize(self.device)
+        self._keep = None
+
+    def configure(self, lo, hi, ghost_layers):
+        self.eng._check(self.eng.lib.sph_slab_configure(self.eng.ctx, int(lo), int(hi), int(ghost_layers)),
+                        "sph_slab_configure")
+
+    def record_views(self):
+        """The 4 exchanged packed arrays as [n_max, 4] float32 views of the engine workspace."""
+        off = (C.c_uint64 * 5)()
+        self.eng._check(self.eng.lib.sph_state_offsets(self.eng.ctx, off), "sph_state_offsets")
+        base = self.eng._ws_ptr - self.eng.workspace.data_ptr()
+        views = []
+        for k in range(RECORD_ARRAYS):
+            b0 = base + int(off[k])
+            views.append(self.eng.workspace[b0:b0 + self.n_max * 16].view(torch.float32).view(self.n_max, 4))
+        return views
+
+    def sort(self, n_local, n_recv):
+        e = self.eng
+        e._check(e.lib.sph_slab_set_counts(e.ctx, int(n_local), int(n_recv)), "sph_slab_set_counts")
+        e._check(e.lib.sph_slab_step(e.ctx, self.info_dev.data_ptr(), 1, e._stream()), "sph_slab_step")
+        return self.info_dev
+
+    def compute(self):
+        e = self.eng
+        e._check(e.lib.sph_slab_compute(e.ctx, e._stream()), "sph_slab_compute")
+
+    def owned_state(self, info_row):
+        """(x, v, x_0) of the owned particles as numpy arrays."""
+        v = self.record_views()
+        b, e_ = int(info_row[1]), int(info_row[4])
+        posm, veld, x0id = v[0][b:e_].cpu().numpy(), v[1][b:e_].cpu().numpy(), v[2][b:e_].cpu().numpy()
+        misc = v[3][b:e_].cpu().numpy().view(np.uint32)
+        ghost = (misc[:, 2] & 4) != 0
+        keep = ~ghost
+        return posm[keep, :3], veld[keep, :3], x0id[keep, :3]
+
+    def launch_count(self):
+        return self.eng.launch_count()
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.device)
+
+
+class SlabSimulation:
+    """The sharded step protocol; see the module docstring."""
+
+    def __init__(self, backend, slabs, rank, world, group=None):
+        self.b = backend
+        self.slabs = slabs
+        self.rank, self.world = rank, world
+        self.group = group
+        self.lo, self.hi = slabs[rank]
+        self.info_all = None  # host copy of every rank's info row
+        self._pending = None
+        self.halo_bytes = 0
+        self.steps_done = 0
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _gather_info(self, info_dev):
+        """all_gather the info rows; the host copy is awaited lazily at the next step."""
+        if self.world == 1:
+            gathered = info_dev.clone().view(1, 8)
+        else:
+            gathered = torch.empty((self.world, 8), dtype=info_dev.dtype, device=info_dev.device)
+            dist.all_gather_into_tensor(gathered.view(-1), info_dev, group=self.group)
+        if gathered.is_cuda:
+            host = torch.empty((self.world, 8), dtype=gathered.dtype).pin_memory()
+            host.copy_(gathered, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pending = (host, ev, gathered)
+        else:
+            self._pending = (gathered, None, None)
+
+    def _await_info(self):
+        host, ev, _ = self._pending
+        if ev is not None:
+            ev.synchronize()
+        self.info_all = host.numpy().copy()
+        st = int(self.info_all[:, 7].max())
+        if st & 1:
+            raise RuntimeError("a particle left the grid (NaN or outside [0, domain))")
+
+    def initialize(self, n_initial):
+        self.b.configure(self.lo, self.hi, GHOST_LAYERS)
+        info = self.b.sort(n_initial, 0)
+        self._gather_info(info)
+
+    def step(self):
+        self._await_info()
+        me = self.info_all[self.rank]
+        n_live = int(me[0])
+        left, right = self.rank - 1, self.rank + 1
+        n_from_left = int(self.info_all[left][4] - self.info_all[left][3]) if left >= 0 else 0
+        n_from_right = int(self.info_all[right][2] - self.info_all[right][1]) if right < self.world else 0
+        sl0, sl1, sr0, sr1 = (int(v) for v in me[1:5])
+        if n_live + n_from_left + n_from_right > self.b.n_max:
+            raise RuntimeError(f"rank {self.rank}: slab capacity exceeded ({n_live}+{n_from_left}+{n_from_right} > "
+                               f"{self.b.n_max}); raise capacity_factor")
+        views = self.b.record_views()
+        ops = []
+        a0 = n_live
+        a1 = n_live + n_from_left
+        for arr in views:
+            if left >= 0:
+                if sl1 > sl0:
+                    ops.append(dist.P2POp(dist.isend, arr[sl0:sl1], left, self.group))
+                if n_from_left:
+                    ops.append(dist.P2POp(dist.irecv, arr[a0:a0 + n_from_left], left, self.group))
+            if right < self.world:
+                if sr1 > sr0:
+                    ops.append(dist.P2POp(dist.isend, arr[sr0:sr1], right, self.group))
+                if n_from_right:
+                    ops.append(dist.P2POp(dist.irecv, arr[a1:a1 + n_from_right], right, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        self.halo_bytes += 16 * RECORD_ARRAYS * (n_from_left + n_from_right)
+        info = self.b.sort(n_live, n_from_left + n_from_right)
+        self._gather_info(info)
+        self.b.compute()
+        self.steps_done += 1
+
+    def owned_state(self):
+        self._await_info()
+        return self.b.owned_state(self.info_all[self.rank])
+
+    def owned_count(self):
+        self._await_info()
+        return int(self.info_all[self.rank][6])
+
+
+def select_owned(arrays, h, lo, hi):
+    lay = layer_of(arrays["x"], h)
+    m = (lay >= lo) & (lay < hi)
+    return {k: v[m] for k, v in arrays.items()}, int(m.sum())
+
+
+def build_sharded(scene_dict, rank, world, device, group=None, capacity_factor=1.35):
+    """Assemble the scene on every rank, plan the slabs from the initial layer histogram and load
+    this rank's share into a CUDA engine.  Returns (SlabSimulation, n_total)."""
+    from .config_builder import SimConfig
+    from .scene import assemble_particles
+
+    cfg = SimConfig(scene_dict)
+    radius = cfg.get_cfg("particleRadius")
+    h = radius * 4.0
+    arrays, _, _, counts = assemble_particles(cfg, 3, 2 * radius)
+    ds = np.array(cfg.get_cfg("domainEnd"), dtype=np.float64) - np.array(cfg.get_cfg("domainStart"))
+    gx = int(np.ceil(ds / h).astype(int)[0])
+    lay = layer_of(arrays["x"], h)
+    hist = np.bincount(lay, minlength=gx)[:gx]
+    slabs = plan_slabs(hist, world)
+    lo, hi = slabs[rank]
+    mine, n_mine = select_owned(arrays, h, lo, hi)
+    ghost_est = int(hist[max(lo - GHOST_LAYERS - 1, 0):lo].sum() + hist[hi:hi + GHOST_LAYERS + 1].sum())
+    n_max = int((n_mine + ghost_est) * capacity_factor) + 1024
+    backend = EngineBackend(cfg, n_max, device)
+    backend.load(mine)
+    sim = SlabSimulation(backend, slabs, rank, world, group)
+    sim.initialize(n_mine)
+    return sim, counts["total"]
+
+
+# -----------------------------------------------------------------------------------------------
+# bench.py --gpus N (launched by torchrun, one rank per GPU)
+# -----------------------------------------------------------------------------------------------
+def bench_main(args):
+    import bench as _bench  # the repo-root module: shared helpers
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} needs WORLD_SIZE={args.gpus} (launch with torch.distributed.run); "
+                         f"got WORLD_SIZE={world}")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    name, sc = _bench.scene_for(world, args.scene)
+    sim, n_total = build_sharded(sc, rank, world, dev)
+    K, W = args.steps, args.warmup
+    for _ in range(W):
+        sim.step()
+    sim.b.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = _bench.ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    halo0, launches0 = sim.halo_bytes, sim.b.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(K):
+        sim.step()
+    b.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([a.elapsed_time(b)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    owned = torch.tensor([sim.owned_count(), sim.halo_bytes - halo0, sim.b.launch_count() - launches0], device=dev,
+                         dtype=torch.float64)
+    tot = owned.clone()
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    mx = owned.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        t_ms = float(ms.item())
+        val = K / (t_ms * 1e-3)
+        halo_per_step = float(tot[1].item()) / K
+        line = {
+            "metric": "SPH steps/sec", "value": val, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak" if name == "box_16m" else "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "m_particle_updates_per_s": val * n_total / 1e6,
+            "config": {"workload": name, "particles": n_total, "solver": "WCSPH", "dt": sc["Configuration"]["timeStepSize"],
+                       "parallelism": f"x-slab x{world}, 2 ghost layers, 1 NCCL send/recv group per step",
+                       "slabs": [list(map(int, s)) for s in sim.slabs], "owned_total": int(tot[0].item()),
+                       "owned_max_per_rank": int(mx[0].item()),
+                       "l2": "per-rank working set (> 126 MB of packed state + neighbour lists) exceeds L2; no flush"},
+            "halo": {"bytes_per_step_all_ranks": halo_per_step,
+                     "fraction_of_owned_state": halo_per_step / (64.0 * max(tot[0].item(), 1.0))},
+            "clocks": clocks,
+            "e2e": None, "gpu_launches": int(tot[2].item()),
+            "roofline": None, "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
