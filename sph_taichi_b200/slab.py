@@ -262,7 +262,9 @@ def build_sharded(scene_dict, rank, world, device, group=None, capacity_factor=1
     slabs = plan_slabs(hist, world)
     lo, hi = slabs[rank]
     mine, n_mine = select_owned(arrays, h, lo, hi)
-    ghost_est = int(hist[max(lo - GHOST_LAYERS - 1, 0):lo].sum() + hist[hi:hi + GHOST_LAYERS + 1].sum())
+    # live ghosts (2 layers per side) + the records received each step (3 layers per side); the
+    # fullest layer bounds every layer the front may reach later
+    ghost_est = 2 * (2 * GHOST_LAYERS + 1) * int(hist.max())
     n_max = int((n_mine + ghost_est) * capacity_factor) + 1024
     backend = EngineBackend(cfg, n_max, device)
     backend.load(mine)

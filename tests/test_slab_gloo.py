@@ -142,7 +142,7 @@ def _worker(rank, world, port, scene_dict, steps, out_dir):
         slabs = slab.plan_slabs(hist, world)
         lo, hi = slabs[rank]
         mine, n_mine = slab.select_owned(arrays, h, lo, hi)
-        backend = OracleSlabBackend(scene_dict, n_max=counts["total"] + 16)
+        backend = OracleSlabBackend(scene_dict, n_max=2 * counts["total"] + 16)
         backend.load(mine)
         sim = slab.SlabSimulation(backend, slabs, rank, world)
         sim.initialize(n_mine)
