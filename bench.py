@@ -28,6 +28,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+METRIC = "M particle-updates/sec (SPH steps/sec x particles)"
+UNIT = "M particle-updates/s"
 FORCE_BYTES_PER_PARTICLE = 52  # algorithmic bytes of the force pass
 HBM_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md
 
@@ -63,7 +65,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -110,7 +112,7 @@ def time_cpu_oracle(scene_dict, budget_s=20.0, max_steps=200):
     for _ in range(k):
         o.step()
     dt = time.perf_counter() - t0
-    return {"value": k / dt, "unit": "steps/s", "cores": cores, "kind": "port",
+    return {"value": k / dt * o.n / 1e6, "unit": UNIT, "steps_per_s": k / dt, "cores": cores, "kind": "port",
             "sample": f"{k} full steps of the same scene ({o.n} particles) after 2 warm-up steps, "
                       f"OpenMP on {cores} host threads; restatement of the reference kernels, not Taichi's ti.cpu codegen"}, o.n
 
@@ -139,15 +141,15 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = k / dt
     line = {
-        "impl": "reference", "metric": "SPH steps/sec", "value": val, "unit": "steps/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": val * o.n / 1e6, "unit": UNIT, "steps_per_s": val,
+        "n_gpus": args.gpus,
         "steps": k, "warmup": warm, "requested_steps": args.steps, "ms_per_step": 1e3 * dt / k,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "m_particle_updates_per_s": val * o.n / 1e6,
         "config": {"workload": name, "particles": o.n, "solver": "WCSPH", "dt": sc["Configuration"]["timeStepSize"]},
-        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": val * o.n / 1e6, "unit": UNIT, "steps_per_s": val, "cores": cores, "kind": "port",
                          "sample": f"{k} full steps of {name} ({o.n} particles) on {cores} host threads (OpenMP C "
                                    "restatement of the reference; Taichi cannot be installed offline)"},
-        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": val * o.n / 1e6, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -231,11 +233,11 @@ def run_single(args):
 
     val = K / (cold_ms * 1e-3)
     line = {
-        "metric": "SPH steps/sec", "value": val, "unit": "steps/s", "n_gpus": 1, "steps": K, "warmup": W,
-        "ms_per_step": cold_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": val * n / 1e6, "unit": UNIT, "steps_per_s": val, "n_gpus": 1, "steps": K,
+        "warmup": W, "ms_per_step": cold_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "m_particle_updates_per_s": val * n / 1e6,
-        "steady": {"value": K / (steady_ms * 1e-3), "unit": "steps/s", "ms_per_step": steady_ms / K,
+        "steady": {"value": K / (steady_ms * 1e-3) * n / 1e6, "unit": UNIT, "steps_per_s": K / (steady_ms * 1e-3),
+                   "ms_per_step": steady_ms / K,
                    "note": "back-to-back CUDA-graph steps, state L2-resident (no flush)"},
         "readme_rtx3090_steps_per_s": 280.0 if name == "dragon_bath" else None,
         "config": {"workload": name, "particles": n, "fluid_particles": ps.fluid_particle_num,
@@ -243,7 +245,8 @@ def run_single(args):
                    "l2": "flushed between timed steps (256 MiB write); 'steady' is un-flushed",
                    "parallelism": "single GPU"},
         "clocks": clocks,
-        "e2e": {"value": Ke / e2e_s, "unit": "steps/s", "steps": Ke, "h2d_bytes_per_step": int(n * 24),
+        "e2e": {"value": Ke / e2e_s * n / 1e6, "unit": UNIT, "steps_per_s": Ke / e2e_s, "steps": Ke,
+                "h2d_bytes_per_step": int(n * 24),
                 "d2h_bytes_per_step": int(n * 24),
                 "note": "ParticleSystem.upload_state -> WCSPHSolver.step -> download_state, pinned host x and v"},
         "gpu_launches": int(launches),

@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -80,6 +81,7 @@ struct SphCtx {
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     int64_t graph_kernels[2] = {0, 0};
     int parity = 0;
+    int var_density = 7, var_force = 1;  // production kernels; SPH_DENSITY_VARIANT / SPH_FORCE_VARIANT select the ablation variants
     cudaStream_t capture_stream = nullptr;  // graphs are captured here (the legacy stream cannot capture)
     bool built = false;  // neighbour structure valid for current positions
 };
@@ -205,6 +207,33 @@ int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *k
     return SPH_OK;
 }
 
+void launch_pair_density(SphCtx *c, cudaStream_t st) {
+    const DevParams &P = c->P;
+    switch (c->var_density) {
+        case 1: k_density_list_b<4, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
+        case 2: k_density_list_b<4, 64><<<blocks_for(P.n, 64), 64, 0, st>>>(P, c->S); break;
+        case 3: k_density_list_b<2, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
+        case 4: k_density_list_b<8, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
+        case 5: k_density_list_b<4, 256><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S); break;
+        case 7: k_density_tma2<<<blocks_for(P.n, DENS_WARPS * 32), DENS_WARPS * 32, 0, st>>>(P, c->S); break;
+        case 6: k_density_tma<<<blocks_for(P.n, DENS_WARPS * 32), DENS_WARPS * 32, 0, st>>>(P, c->S); break;
+        case 0: k_density_list<true><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
+        default: k_density_tma2<<<blocks_for(P.n, DENS_WARPS * 32), DENS_WARPS * 32, 0, st>>>(P, c->S); break;
+    }
+}
+void launch_pair_force(SphCtx *c, cudaStream_t st) {
+    const DevParams &P = c->P;
+    switch (c->var_force) {
+        case 1: k_force_list_b<4, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
+        case 2: k_force_list_b<4, 64><<<blocks_for(P.n, 64), 64, 0, st>>>(P, c->S); break;
+        case 3: k_force_list_b<2, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
+        case 4: k_force_list_b<8, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
+        case 5: k_force_list_b<4, 256><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S); break;
+        case 0: k_force_list<<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
+        default: k_force_list_b<4, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
+    }
+}
+
 int launch_boundary_volume(SphCtx *c, int moving, cudaStream_t st, int64_t *kernels) {
     const DevParams &P = c->P;
     if (P.n_solid == 0) return SPH_OK;
@@ -234,9 +263,9 @@ int launch_step(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels) {
     if (tm) tm->mark(T_BVOL);
     if (c->has_dynamic_solids) { rc = launch_boundary_volume(c, 1, st, kernels); if (rc) return rc; }
     if (tm) tm->mark(T_DENSITY);
-    k_density_list<true><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
+    launch_pair_density(c, st);
     if (tm) tm->mark(T_FORCE);
-    k_force_list<<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
+    launch_pair_force(c, st);
     if (tm) tm->mark(T_ADVECT);
     k_advect<true><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
     *kernels += 3;
@@ -291,6 +320,8 @@ int sph_create(const SphParams *params, int64_t n_max, int64_t n_solid, int32_t 
     c->L = make_layout(n_max, C, n_solid, n_bodies);
     if (c->L.total > workspace_bytes) { delete c; return fail(nullptr, SPH_E_CAPACITY, "workspace too small"); }
     c->ws = static_cast<char *>(workspace);
+    if (const char *v = std::getenv("SPH_DENSITY_VARIANT")) c->var_density = std::atoi(v);
+    if (const char *v = std::getenv("SPH_FORCE_VARIANT")) c->var_force = std::atoi(v);
     c->P = DevParams{};
     derive_params(c);
     c->P.n = 0;
@@ -576,8 +607,8 @@ int sph_slab_compute(SphCtx *ctx, void *stream) {
     if (P.n == 0) return SPH_OK;
     if (!ctx->built) return fail(ctx, SPH_E_ARG, "sph_slab_compute needs a fresh sph_slab_step(sort_only = 1)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    k_density_list<true><<<blocks_for(P.n, 128), 128, 0, st>>>(P, ctx->S);
-    k_force_list<<<blocks_for(P.n, 128), 128, 0, st>>>(P, ctx->S);
+    launch_pair_density(ctx, st);
+    launch_pair_force(ctx, st);
     k_advect<true><<<blocks_for(P.n, 256), 256, 0, st>>>(P, ctx->S);
     ctx->launches += 3;
     ctx->built = false;

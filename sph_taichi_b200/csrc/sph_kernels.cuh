@@ -744,3 +744,501 @@ __global__ void __launch_bounds__(128) k_force_list(DevParams P, DevArrays S) {
     }
     S.acc[i] = make_float4(A.npx + A.prx, A.npy + A.pry, A.npz + A.prz, 0.f);
 }
+
+// =====================================================================================
+// pair kernels v2b: the dense list loops in batches of B neighbours with all gathers of a batch
+// issued before any arithmetic (ncu on v2: both list loops stall on long_scoreboard, i.e. they are
+// latency-bound on the dependent list -> gather chain).  Tails are padded with the particle
+// itself, whose pair terms are exactly zero.
+// =====================================================================================
+__device__ __forceinline__ void force_pair_pre(const DevParams &P, const DevArrays &S, ForceAcc &A, int j, float rx,
+                                               float ry, float rz, float r2, float mVj, const float4 &aj,
+                                               const float4 &vj, const float4 &vi, float dpi, float dpi_solid,
+                                               float coh_i) {
+    float r, inv_r;
+    fast_norm(r2, r, inv_r);
+    float gs = gradw_scale_fast(P, r, inv_r);
+    if (aj.z > 0.0f) {
+        float w = (r2 > P.d2) ? w_cubic(P, r) : P.w_diam;
+        float c = coh_i * aj.z;
+        A.npx -= c * rx * w; A.npy -= c * ry * w; A.npz -= c * rz * w;
+        float vxy = (vi.x - vj.x) * rx + (vi.y - vj.y) * ry + (vi.z - vj.z) * rz;
+        float sv = __fdividef(P.d_visc * aj.x * vxy, r * r + P.visc_eps) * gs;
+        A.npx += sv * rx; A.npy += sv * ry; A.npz += sv * rz;
+        float cp = -P.rho0 * mVj * (dpi + aj.y) * gs;
+        A.prx += cp * rx; A.pry += cp * ry; A.prz += cp * rz;
+    } else {
+        float cp = -P.rho0 * mVj * dpi_solid * gs;
+        float fx = cp * rx, fy = cp * ry, fz = cp * rz;
+        A.prx += fx; A.pry += fy; A.prz += fz;
+        if (aj.z < -1.5f) {
+            float *a = reinterpret_cast<float *>(S.acc + j);
+            atomicAdd(a + 0, -fx * P.rho0 / aj.x);
+            atomicAdd(a + 1, -fy * P.rho0 / aj.x);
+            atomicAdd(a + 2, -fz * P.rho0 / aj.x);
+        }
+    }
+}
+
+template <int B, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_force_list_b(DevParams P, DevArrays S) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    if (P.slab_on && S.grid_ids[i] >= P.C) return;
+    float4 mi = S.misc[i];
+    uint32_t fl = __float_as_uint(mi.z);
+    if (!(fl & FLAG_FLUID)) return;
+    if (fl & FLAG_GHOST) return;
+    float4 pi = S.posm[i];
+    float4 vi = S.veld[i];
+    float4 ai = S.aux[i];
+    const float dpi = ai.y;
+    const float dpi_solid = dpi + mi.y * P.inv_rho0sq;
+    const float coh_i = P.sigma / mi.x;
+    ForceAcc A = {P.gx_, P.gy_, P.gz_, 0.f, 0.f, 0.f};
+    const int cnt = S.nbr_cnt[i];
+    if (cnt != NBR_OVERFLOW) {
+        const int32_t *lp = S.nbr_list + i;
+        const size_t stride = (size_t)S.npad;
+        for (int k0 = 0; k0 < cnt; k0 += B) {
+            int j[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) j[u] = (k0 + u < cnt) ? lp[(size_t)(k0 + u) * stride] : i;
+            float4 pj[B], aj[B], vj[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                pj[u] = __ldg(S.posm + j[u]);
+                aj[u] = __ldg(S.aux + j[u]);
+                vj[u] = __ldg(S.veld + j[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
+                float r2 = rx * rx + ry * ry + rz * rz;
+                force_pair_pre(P, S, A, j[u], rx, ry, rz, r2, pj[u].w, aj[u], vj[u], vi, dpi, dpi_solid, coh_i);
+            }
+        }
+    } else {
+        for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
+                          [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
+                              force_pair(P, S, A, j, rx, ry, rz, r2, pj.w, vi, dpi, dpi_solid, coh_i);
+                          });
+    }
+    S.acc[i] = make_float4(A.npx + A.prx, A.npy + A.pry, A.npz + A.prz, 0.f);
+}
+
+template <int B, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_density_list_b(DevParams P, DevArrays S) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    if (P.slab_on && S.grid_ids[i] >= P.C) return;
+    float4 pi = S.posm[i];
+    float4 mi = S.misc[i];
+    uint32_t fl = __float_as_uint(mi.z);
+    if (!(fl & FLAG_FLUID)) {
+        bool dyn = (fl & FLAG_DYNAMIC) != 0;
+        S.aux[i] = make_float4(S.veld[i].w, 0.0f, dyn ? -2.0f : -1.0f, 0.0f);
+        S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        S.nbr_cnt[i] = 0;
+        return;
+    }
+    int cnt = 0;
+    {
+        int32_t *lp = S.nbr_list + i;
+        const size_t stride = (size_t)S.npad;
+        int ci, cj, ck;
+        cell_of(P, pi.x, pi.y, pi.z, ci, cj, ck);
+        ci = min(max(ci, 0), P.gx - 1); cj = min(max(cj, 0), P.gy - 1); ck = min(max(ck, 0), P.gz - 1);
+        int k_lo = max(ck - 1, 0), k_hi = min(ck + 1, P.gz - 1);
+        for (int dx = -1; dx <= 1; ++dx) {
+            int ni = ci + dx;
+            if (ni < 0 || ni >= P.gx) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                int nj = cj + dy;
+                if (nj < 0 || nj >= P.gy) continue;
+                int row = (ni * P.gy + nj) * P.gz;
+                int j0 = __ldg(S.cell_end + max(row + k_lo - 1, 0));
+                int j1 = __ldg(S.cell_end + row + k_hi);
+                for (int jb = j0; jb < j1; jb += B) {
+                    float4 pj[B];
+#pragma unroll
+                    for (int u = 0; u < B; ++u) pj[u] = __ldg(S.posm + min(jb + u, j1 - 1));
+#pragma unroll
+                    for (int u = 0; u < B; ++u) {
+                        int j = jb + u;
+                        float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
+                        float r2 = rx * rx + ry * ry + rz * rz;
+                        bool hit = (r2 < P.h2) && (j != i) && (j < j1);
+                        if (hit) {
+                            if (cnt < NBR_CAP) { *lp = j; lp += stride; }
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    float den = 0.0f;
+    if (cnt <= NBR_CAP) {
+        S.nbr_cnt[i] = cnt;
+        const int32_t *lp = S.nbr_list + i;
+        const size_t stride = (size_t)S.npad;
+        for (int k0 = 0; k0 < cnt; k0 += B) {
+            float4 pj[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                int j = (k0 + u < cnt) ? lp[(size_t)(k0 + u) * stride] : i;
+                pj[u] = __ldg(S.posm + j);
+            }
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
+                float r2 = rx * rx + ry * ry + rz * rz;
+                float r, inv_r;
+                fast_norm(r2, r, inv_r);
+                float w = pj[u].w * w_cubic(P, r);
+                den += (k0 + u < cnt) ? w : 0.0f;
+            }
+        }
+    } else {
+        S.nbr_cnt[i] = NBR_OVERFLOW;
+        for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
+                          [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
+                              den += pj.w * w_cubic(P, sqrtf(r2));
+                          });
+    }
+    float rho = pi.w * P.w0;
+    rho += den;
+    rho *= P.rho0;
+    float vol = mi.x / rho;
+    float rc = fmaxf(rho, P.rho0);
+    float p = tait_pressure(P, rc);
+    reinterpret_cast<float *>(S.veld + i)[3] = rc;
+    reinterpret_cast<float *>(S.misc + i)[1] = p;
+    S.aux[i] = make_float4(vol, p / (rc * rc), mi.x, 0.0f);
+}
+
+// =====================================================================================
+// density pass v3: TMA-staged candidate windows.
+//
+// ncu on v2 (profiles/r01_v2_pair_kernels_ncu.txt): the candidate scan is co-limited by L1/TEX
+// (76 % of peak) -- the 32 particles of a warp sit in ~4-5 cells, so every per-lane LDG.128 of a
+// candidate touches 4-5 different 128-byte lines (one L1 tag cycle each).  Here each WARP stages,
+// per (dx, dy) column, the union of its lanes' candidate ranges -- one contiguous run of the
+// sorted posm array, ~0.75-1.5 KB -- into shared memory with ONE bulk async copy
+// (cp.async.bulk global -> shared, completion on an mbarrier; SASS: UBLKCP), double-buffered
+// across the 9 columns, and the lanes then scan their own sub-range with LDS.128.
+// Windows longer than WIN_CAP (sparse splashes) fall back to the direct global scan.
+// =====================================================================================
+constexpr int WIN_CAP = 128;      // particles per staged window (2 KB)
+constexpr int DENS_WARPS = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared::cta, bytes multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(DENS_WARPS * 32) k_density_tma(DevParams P, DevArrays S) {
+    __shared__ __align__(128) float4 s_win[DENS_WARPS][2][WIN_CAP];
+    __shared__ __align__(8) uint64_t s_bar[DENS_WARPS][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane == 0) { mbar_init(&s_bar[warp][0], 1); mbar_init(&s_bar[warp][1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+
+    bool live = i < P.n && !(P.slab_on && S.grid_ids[min(i, P.n - 1)] >= P.C);
+    float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), mi = pi;
+    uint32_t fl = 0;
+    if (live) { pi = S.posm[i]; mi = S.misc[i]; fl = __float_as_uint(mi.z); }
+    const bool fluid = live && (fl & FLAG_FLUID);
+    if (live && !fluid) {
+        bool dyn = (fl & FLAG_DYNAMIC) != 0;
+        S.aux[i] = make_float4(S.veld[i].w, 0.0f, dyn ? -2.0f : -1.0f, 0.0f);
+        S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        S.nbr_cnt[i] = 0;
+    }
+    if (__ballot_sync(0xffffffffu, fluid) == 0u) return;  // warp-uniform
+
+    int ci = 0, cj = 0, ck = 0;
+    cell_of(P, pi.x, pi.y, pi.z, ci, cj, ck);
+    ci = min(max(ci, 0), P.gx - 1); cj = min(max(cj, 0), P.gy - 1); ck = min(max(ck, 0), P.gz - 1);
+    const int k_lo = max(ck - 1, 0), k_hi = min(ck + 1, P.gz - 1);
+
+    // per-lane candidate range of column c = (dx + 1) * 3 + (dy + 1), reference visiting order
+    auto col_range = [&](int c, int &j0, int &j1) {
+        int ni = ci + c / 3 - 1, nj = cj + c % 3 - 1;
+        j0 = 0; j1 = 0;
+        if (fluid && ni >= 0 && ni < P.gx && nj >= 0 && nj < P.gy) {
+            int row = (ni * P.gy + nj) * P.gz;
+            j0 = __ldg(S.cell_end + max(row + k_lo - 1, 0));
+            j1 = __ldg(S.cell_end + row + k_hi);
+        }
+    };
+    // warp-uniform window [J0, J1) of column c and its staging into buffer b; returns the mode:
+    // 0 = empty, 1 = staged (wait on the barrier), 2 = too long, scan global memory directly
+    uint32_t phase = 0u;  // bit b = parity of the next completion of barrier b
+    auto stage = [&](int j0, int j1, int b, int &J0, int &J1) -> int {
+        bool ne = j1 > j0;
+        J0 = __reduce_min_sync(0xffffffffu, ne ? j0 : 0x7fffffff);
+        J1 = __reduce_max_sync(0xffffffffu, ne ? j1 : 0);
+        if (J1 <= J0) return 0;
+        if (J1 - J0 > WIN_CAP) return 2;
+        if (lane == 0) {
+            uint32_t bytes = (uint32_t)(J1 - J0) * 16u;
+            mbar_expect_tx(&s_bar[warp][b], bytes);
+            tma_bulk_g2s(&s_win[warp][b][0], S.posm + J0, bytes, &s_bar[warp][b]);
+        }
+        return 1;
+    };
+
+    int cnt = 0;
+    int32_t *lp = S.nbr_list + (fluid ? i : 0);
+    const size_t stride = (size_t)S.npad;
+    auto test = [&](int j, const float4 &pj) {
+        float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+        float r2 = rx * rx + ry * ry + rz * rz;
+        if (r2 < P.h2 && j != i) {
+            if (cnt < NBR_CAP) { *lp = j; lp += stride; }
+            ++cnt;
+        }
+    };
+
+    int j0n, j1n, J0n, J1n;
+    col_range(0, j0n, j1n);
+    int mode_n = stage(j0n, j1n, 0, J0n, J1n);
+    for (int c = 0; c < 9; ++c) {
+        const int b = c & 1;
+        const int j0 = j0n, j1 = j1n, J0 = J0n, mode = mode_n;
+        if (c + 1 < 9) {
+            col_range(c + 1, j0n, j1n);
+            __syncwarp();  // every lane is done reading buffer b^1 (column c - 1)
+            mode_n = stage(j0n, j1n, b ^ 1, J0n, J1n);
+        }
+        if (mode == 1) {
+            mbar_wait(&s_bar[warp][b], (phase >> b) & 1u);
+            phase ^= 1u << b;
+            const float4 *w = &s_win[warp][b][0] - J0;
+#pragma unroll 4
+            for (int j = j0; j < j1; ++j) test(j, w[j]);
+        } else if (mode == 2) {
+#pragma unroll 4
+            for (int j = j0; j < j1; ++j) test(j, __ldg(S.posm + j));
+        }
+    }
+    if (!fluid) return;
+
+    float den = 0.0f;
+    if (cnt <= NBR_CAP) {
+        S.nbr_cnt[i] = cnt;
+        const int32_t *lq = S.nbr_list + i;
+        for (int k0 = 0; k0 < cnt; k0 += 4) {
+            float4 pj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int j = (k0 + u < cnt) ? lq[(size_t)(k0 + u) * stride] : i;
+                pj[u] = __ldg(S.posm + j);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
+                float r2 = rx * rx + ry * ry + rz * rz;
+                float r, inv_r;
+                fast_norm(r2, r, inv_r);
+                float wv = pj[u].w * w_cubic(P, r);
+                den += (k0 + u < cnt) ? wv : 0.0f;
+            }
+        }
+    } else {
+        S.nbr_cnt[i] = NBR_OVERFLOW;
+        for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
+                          [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
+                              den += pj.w * w_cubic(P, sqrtf(r2));
+                          });
+    }
+    float rho = pi.w * P.w0;
+    rho += den;
+    rho *= P.rho0;
+    float vol = mi.x / rho;
+    float rc = fmaxf(rho, P.rho0);
+    float p = tait_pressure(P, rc);
+    reinterpret_cast<float *>(S.veld + i)[3] = rc;
+    reinterpret_cast<float *>(S.misc + i)[1] = p;
+    S.aux[i] = make_float4(vol, p / (rc * rc), mi.x, 0.0f);
+}
+
+// =====================================================================================
+// density pass v4: v3 + branch-free candidate scan.  The SASS of v3 spends ~10 of ~21
+// instructions per candidate in the divergent "append to list" branch (BSSY/BRA/STG/LEA/BSYNC,
+// taken by nearly every warp iteration because some lane almost always hits).  v4 scans 32
+// candidates at a time into a per-lane hit bitmask (one predicated LOP3 per candidate, no
+// branch, no store) and then flushes the set bits to the list in a short loop.
+// =====================================================================================
+template <bool FROM_SMEM>
+__device__ __forceinline__ uint32_t scan_chunk(const DevParams &P, const float4 *__restrict__ src, int jb, int len,
+                                               int j_last, float xi, float yi, float zi) {
+    uint32_t m = 0u;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (g * 8 < len) {
+#pragma unroll
+            for (int u = g * 8; u < g * 8 + 8; ++u) {
+                float4 pj = FROM_SMEM ? src[jb + u] : __ldg(src + min(jb + u, j_last));
+                float rx = xi - pj.x, ry = yi - pj.y, rz = zi - pj.z;
+                float r2 = rx * rx + ry * ry + rz * rz;
+                m |= (r2 < P.h2) ? (1u << u) : 0u;
+            }
+        }
+    }
+    return (len >= 32) ? m : (m & ((1u << len) - 1u));
+}
+
+__global__ void __launch_bounds__(DENS_WARPS * 32) k_density_tma2(DevParams P, DevArrays S) {
+    __shared__ __align__(128) float4 s_win[DENS_WARPS][2][WIN_CAP + 32];
+    __shared__ __align__(8) uint64_t s_bar[DENS_WARPS][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane == 0) { mbar_init(&s_bar[warp][0], 1); mbar_init(&s_bar[warp][1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+
+    bool live = i < P.n && !(P.slab_on && S.grid_ids[min(i, P.n - 1)] >= P.C);
+    float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), mi = pi;
+    uint32_t fl = 0;
+    if (live) { pi = S.posm[i]; mi = S.misc[i]; fl = __float_as_uint(mi.z); }
+    const bool fluid = live && (fl & FLAG_FLUID);
+    if (live && !fluid) {
+        bool dyn = (fl & FLAG_DYNAMIC) != 0;
+        S.aux[i] = make_float4(S.veld[i].w, 0.0f, dyn ? -2.0f : -1.0f, 0.0f);
+        S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        S.nbr_cnt[i] = 0;
+    }
+    if (__ballot_sync(0xffffffffu, fluid) == 0u) return;
+
+    int ci = 0, cj = 0, ck = 0;
+    cell_of(P, pi.x, pi.y, pi.z, ci, cj, ck);
+    ci = min(max(ci, 0), P.gx - 1); cj = min(max(cj, 0), P.gy - 1); ck = min(max(ck, 0), P.gz - 1);
+    const int k_lo = max(ck - 1, 0), k_hi = min(ck + 1, P.gz - 1);
+    auto col_range = [&](int c, int &j0, int &j1) {
+        int ni = ci + c / 3 - 1, nj = cj + c % 3 - 1;
+        j0 = 0; j1 = 0;
+        if (fluid && ni >= 0 && ni < P.gx && nj >= 0 && nj < P.gy) {
+            int row = (ni * P.gy + nj) * P.gz;
+            j0 = __ldg(S.cell_end + max(row + k_lo - 1, 0));
+            j1 = __ldg(S.cell_end + row + k_hi);
+        }
+    };
+    uint32_t phase = 0u;
+    auto stage = [&](int j0, int j1, int b, int &J0, int &J1) -> int {
+        bool ne = j1 > j0;
+        J0 = __reduce_min_sync(0xffffffffu, ne ? j0 : 0x7fffffff);
+        J1 = __reduce_max_sync(0xffffffffu, ne ? j1 : 0);
+        if (J1 <= J0) return 0;
+        if (J1 - J0 > WIN_CAP) return 2;
+        if (lane == 0) {
+            uint32_t bytes = (uint32_t)(J1 - J0) * 16u;
+            mbar_expect_tx(&s_bar[warp][b], bytes);
+            tma_bulk_g2s(&s_win[warp][b][0], S.posm + J0, bytes, &s_bar[warp][b]);
+        }
+        return 1;
+    };
+
+    int cnt = 0;
+    uint32_t widx = (uint32_t)(fluid ? i : 0);                    // index of the next list slot
+    const uint32_t widx_cap = widx + (uint32_t)(NBR_CAP - 1) * (uint32_t)S.npad;  // last row
+    auto flush = [&](uint32_t m, int jb) {
+        if ((uint32_t)(i - jb) < 32u) m &= ~(1u << (i - jb));  // p_i != p_j
+        while (m) {
+            int b = __ffs(m) - 1;
+            m &= m - 1u;
+            S.nbr_list[widx] = jb + b;           // beyond NBR_CAP the last row is overwritten (flagged below)
+            widx = min(widx + (uint32_t)S.npad, widx_cap);
+            ++cnt;
+        }
+    };
+
+    int j0n, j1n, J0n, J1n;
+    col_range(0, j0n, j1n);
+    int mode_n = stage(j0n, j1n, 0, J0n, J1n);
+    for (int c = 0; c < 9; ++c) {
+        const int b = c & 1;
+        const int j0 = j0n, j1 = j1n, J0 = J0n, mode = mode_n;
+        if (c + 1 < 9) {
+            col_range(c + 1, j0n, j1n);
+            __syncwarp();
+            mode_n = stage(j0n, j1n, b ^ 1, J0n, J1n);
+        }
+        if (mode == 1) {
+            mbar_wait(&s_bar[warp][b], (phase >> b) & 1u);
+            phase ^= 1u << b;
+            const float4 *w = &s_win[warp][b][0] - J0;
+            for (int jb = j0; jb < j1; jb += 32)
+                flush(scan_chunk<true>(P, w, jb, min(32, j1 - jb), 0, pi.x, pi.y, pi.z), jb);
+        } else if (mode == 2) {
+            for (int jb = j0; jb < j1; jb += 32)
+                flush(scan_chunk<false>(P, S.posm, jb, min(32, j1 - jb), j1 - 1, pi.x, pi.y, pi.z), jb);
+        }
+    }
+    if (!fluid) return;
+
+    float den = 0.0f;
+    const size_t stride = (size_t)S.npad;
+    if (cnt <= NBR_CAP) {
+        S.nbr_cnt[i] = cnt;
+        const int32_t *lq = S.nbr_list + i;
+        for (int k0 = 0; k0 < cnt; k0 += 4) {
+            float4 pj[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int j = (k0 + u < cnt) ? lq[(size_t)(k0 + u) * stride] : i;
+                pj[u] = __ldg(S.posm + j);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
+                float r2 = rx * rx + ry * ry + rz * rz;
+                float r, inv_r;
+                fast_norm(r2, r, inv_r);
+                float wv = pj[u].w * w_cubic(P, r);
+                den += (k0 + u < cnt) ? wv : 0.0f;
+            }
+        }
+    } else {
+        S.nbr_cnt[i] = NBR_OVERFLOW;
+        for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
+                          [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
+                              den += pj.w * w_cubic(P, sqrtf(r2));
+                          });
+    }
+    float rho = pi.w * P.w0;
+    rho += den;
+    rho *= P.rho0;
+    float vol = mi.x / rho;
+    float rc = fmaxf(rho, P.rho0);
+    float p = tait_pressure(P, rc);
+    reinterpret_cast<float *>(S.veld + i)[3] = rc;
+    reinterpret_cast<float *>(S.misc + i)[1] = p;
+    S.aux[i] = make_float4(vol, p / (rc * rc), mi.x, 0.0f);
+}

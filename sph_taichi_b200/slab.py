@@ -325,10 +325,9 @@ def bench_main(args):
         val = K / (t_ms * 1e-3)
         halo_per_step = float(tot[1].item()) / K
         line = {
-            "metric": "SPH steps/sec", "value": val, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak" if name == "box_16m" else "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "m_particle_updates_per_s": val * n_total / 1e6,
+            "metric": _bench.METRIC, "value": val * n_total / 1e6, "unit": _bench.UNIT, "steps_per_s": val,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "particles": n_total, "solver": "WCSPH", "dt": sc["Configuration"]["timeStepSize"],
                        "parallelism": f"x-slab x{world}, 2 ghost layers, 1 NCCL send/recv group per step",
                        "slabs": [list(map(int, s)) for s in sim.slabs], "owned_total": int(tot[0].item()),

@@ -272,3 +272,32 @@ def test_fused_step_fields_vs_oracle_and_overflow_path():
         assert _maxrel(ps.acceleration.to_numpy(), o.acceleration) < 10 * REL
         assert _maxrel(ps.v.to_numpy(), o.v) < 10 * REL
         assert _maxrel(ps.x.to_numpy(), o.x) < 1e-6
+
+
+def _run_slab_check(nproc, extra=()):
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tools", "check_slab_parity.py")
+    if nproc == 1:
+        cmd = [sys.executable, script, *extra]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", script, *extra]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert res.returncode == 0 and lines, res.stdout[-2000:] + res.stderr[-2000:]
+    return json.loads(lines[-1])
+
+
+def test_slab_mode_single_rank_equals_plain_engine():
+    """Slab classification / trash bucket / info ranges with world = 1 (no exchange)."""
+    out = _run_slab_check(1, ["--counts", "40", "16", "16", "--steps", "30"])
+    assert out["ok"] and out["same_particle_set"] and out["max_dx_over_d"] < 1e-4
+
+
+def test_slab_two_gpus_equals_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    out = _run_slab_check(2, ["--counts", "64", "24", "24", "--steps", "60"])
+    assert out["ok"] and out["migrated"] and all(h > 0 for h in out["halo_bytes"])
