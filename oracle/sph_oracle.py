@@ -31,6 +31,11 @@ def build(force: bool = False) -> None:
 _LIBS = {}
 
 
+def set_threads(n: int) -> None:
+    """omp_set_num_threads for the oracle's OpenMP runtime."""
+    C.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+
+
 def _params_struct(real):
     class OracleParams(C.Structure):
         _fields_ = [("n", C.c_int32), ("grid_num", C.c_int32 * 3), ("h", real), ("diameter", real), ("m_V0", real),
@@ -73,7 +78,7 @@ class OracleSim:
         self.creal = C.c_double if f64 else C.c_float
         self.lib = _lib(f64)
         if threads:
-            os.environ["OMP_NUM_THREADS"] = str(threads)
+            set_threads(threads)
 
         # derived constants, all folded in double like the reference's Python scope
         # (particle_system.py:16-46, sph_base.py:11-21, WCSPH.py:8-16)

@@ -301,3 +301,38 @@ def test_slab_two_gpus_equals_single_gpu():
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     out = _run_slab_check(2, ["--counts", "64", "24", "24", "--steps", "60"])
     assert out["ok"] and out["migrated"] and all(h > 0 for h in out["halo_bytes"])
+
+
+def test_armadillo_bath_dynamic_full_size():
+    """BASELINE cfg 3 (1.74 M particles, three dynamic rigid bodies): a few real steps against the
+    oracle, plus size-independent properties (rigidity of the shape-matched bodies, sortedness)."""
+    from oracle.sph_oracle import OracleSim
+    from sph_taichi_b200 import ParticleSystem, SimConfig, scene
+    sc = scene.armadillo_bath_dynamic()
+    ps = ParticleSystem(SimConfig(sc))
+    assert ps.fluid_particle_num == 1723968 and ps.solid_particle_num == 3 * 5490
+    solver = ps.build_solver()
+    solver.initialize()
+    o = OracleSim(sc)
+    o.initialize()
+    for oid in (1, 2, 3):  # fp32 sums of 5490 terms: tree order (engine) vs serial order (oracle)
+        assert _maxrel(ps.rigid_rest_cm[oid], o.rest_cm[oid]) < 1e-4
+    steps = 6
+    solver.step(steps)
+    for _ in range(steps):
+        o.step()
+    assert ps._engine.check_status() == 0
+    x, x0, oid_g = ps.x.to_numpy(), ps.x_0.to_numpy(), ps.object_id.to_numpy()
+    kg, ko = order_by_x0(x0), order_by_x0(o.x_0)
+    # rigid bodies share rest lattices (shifted copies), so key on (object id, x_0)
+    kg = np.lexsort((x0[:, 2], x0[:, 1], x0[:, 0], oid_g)); ko = np.lexsort((o.x_0[:, 2], o.x_0[:, 1], o.x_0[:, 0], o.object_id))
+    assert np.array_equal(x0[kg], o.x_0[ko]) and np.array_equal(oid_g[kg], o.object_id[ko])
+    assert np.abs(x[kg] - o.x[ko]).max() / 0.02 < 1e-3
+    assert _maxrel(ps.v.to_numpy()[kg], o.v[ko]) < 1e-3
+    assert np.all(np.diff(ps.grid_ids.to_numpy()) >= 0)
+    for b in (1, 2, 3):  # shape matching keeps every body congruent to its rest shape
+        sel = oid_g == b
+        p, q = x[sel].astype(np.float64), x0[sel].astype(np.float64)
+        dp = np.linalg.norm(p - p.mean(0), axis=1); dq = np.linalg.norm(q - q.mean(0), axis=1)
+        assert np.abs(dp - dq).max() < 1e-4
+        assert p[:, 1].mean() < q[:, 1].mean()  # and it is falling
