@@ -139,12 +139,14 @@ static inline REAL norm3(const REAL r[3]) { return R_SQRT(r[0] * r[0] + r[1] * r
 /* ---- particle_system.py:311-375 --------------------------------------------------- */
 static void permute_real(REAL *a, const int32_t *dst, int32_t n, int w, void *tmp) {
     REAL *t = (REAL *)tmp;
+#pragma omp parallel for schedule(static)
     for (int32_t i = 0; i < n; ++i)
         for (int c = 0; c < w; ++c) t[(size_t)dst[i] * w + c] = a[(size_t)i * w + c];
     memcpy(a, t, sizeof(REAL) * (size_t)n * w);
 }
 static void permute_i32(int32_t *a, const int32_t *dst, int32_t n, int w, void *tmp) {
     int32_t *t = (int32_t *)tmp;
+#pragma omp parallel for schedule(static)
     for (int32_t i = 0; i < n; ++i)
         for (int c = 0; c < w; ++c) t[(size_t)dst[i] * w + c] = a[(size_t)i * w + c];
     memcpy(a, t, sizeof(int32_t) * (size_t)n * w);
@@ -157,14 +159,17 @@ int oracle_neighbor_build(const OracleParams *P, OracleState *S) {
     const int64_t C = cell_count(P);
     int32_t *cnt = S->grid_particles_num;
     memset(cnt, 0, sizeof(int32_t) * (size_t)C);
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
     for (int32_t i = 0; i < n; ++i) {
         int32_t idx[3];
         pos_to_index(P, S->x + 3 * (size_t)i, idx);
         int32_t c = flatten(P, idx);
-        if (c < 0 || c >= C) return -1;
+        if (c < 0 || c >= C) { bad |= 1; c = 0; }
         S->grid_ids[i] = c;
-        cnt[c] += 1;
     }
+    if (bad) return -1;
+    for (int32_t i = 0; i < n; ++i) cnt[S->grid_ids[i]] += 1; /* serial histogram: deterministic */
     /* PrefixSumExecutor.run: in-place inclusive scan (particle_system.py:374) */
     for (int64_t c = 1; c < C; ++c) cnt[c] += cnt[c - 1];
     /* stable counting sort (serial semantics of particle_system.py:325-330) */
