@@ -50,6 +50,16 @@ def measured_hbm_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_force_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the force kernel, per launch, from the committed
+    ncu --set full capture of the same workload (profiles/force_dram_traffic.json), else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "force_dram_traffic.json")) as fh:
+            return json.load(fh).get(workload, {}).get("bytes_per_launch")
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -269,7 +279,8 @@ def run_single(args):
                 "note": "ParticleSystem.upload_state -> WCSPHSolver.step -> download_state, pinned host x and v"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_force<NP,PR> (fused non-pressure + pressure pass)", "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_force_traffic(name),
                      "peak_source": peak_src, "algorithmic_bytes_per_particle": FORCE_BYTES_PER_PARTICLE,
                      "avg_launch_ms": force_ms, "share_of_step": force_ms / max(stages.get("total", 0.0), 1e-9),
                      "note": "pair kernels are FP32-issue bound (~80-100 flop/B), see DESIGN.md section 5"},

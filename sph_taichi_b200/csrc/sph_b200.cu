@@ -17,6 +17,7 @@ namespace {
 std::string g_create_error;
 
 constexpr int NUM_TIMERS = 12;
+constexpr int GRAPH_UNROLL = 4;  // must be even (ping-pong parity returns to its start)
 const char *kTimerNames[NUM_TIMERS] = {"zero",  "hash",    "scan",  "bucket",    "rank_move", "boundary_volume",
                                        "density", "force", "advect_clamp", "rigid", "unused",    "total"};
 enum { T_ZERO, T_HASH, T_SCAN, T_BUCKET, T_MOVE, T_BVOL, T_DENSITY, T_FORCE, T_ADVECT, T_RIGID, T_UNUSED, T_TOTAL };
@@ -80,6 +81,8 @@ struct SphCtx {
     // CUDA graphs, one per ping-pong parity
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     int64_t graph_kernels[2] = {0, 0};
+    cudaGraphExec_t graph_multi[2] = {nullptr, nullptr};  // GRAPH_UNROLL steps per replay
+    int64_t graph_multi_kernels[2] = {0, 0};
     int parity = 0;
     int var_density = 7, var_force = 1;  // production kernels; SPH_DENSITY_VARIANT / SPH_FORCE_VARIANT select the ablation variants
     cudaStream_t capture_stream = nullptr;  // graphs are captured here (the legacy stream cannot capture)
@@ -164,8 +167,10 @@ inline float *dev_scratch(SphCtx *c) { return reinterpret_cast<float *>(c->ws + 
 inline int blocks_for(int64_t n, int t) { return (int)((n + t - 1) / t); }
 
 void drop_graphs(SphCtx *c) {
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 2; ++k) {
         if (c->graph[k]) { cudaGraphExecDestroy(c->graph[k]); c->graph[k] = nullptr; }
+        if (c->graph_multi[k]) { cudaGraphExecDestroy(c->graph_multi[k]); c->graph_multi[k] = nullptr; }
+    }
 }
 
 // ---- launch sequences -----------------------------------------------------------------
@@ -518,36 +523,50 @@ int sph_solve_constraints(SphCtx *ctx, int32_t body, float *R_out_dev, void *str
     return rigid_call(ctx, body, 2, R_out_dev, stream);
 }
 
+// Capture `nsteps` consecutive steps (starting from the current ping-pong parity) into one graph.
+static int capture_steps(SphCtx *ctx, int nsteps, cudaGraphExec_t *out, int64_t *kernels_out) {
+    const int par = ctx->parity;
+    cudaGraph_t g = nullptr;
+    int64_t kernels = 0;
+    if (!ctx->capture_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = ctx->capture_stream;
+    CUDA_TRY(ctx, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int rc = SPH_OK;
+    for (int s = 0; s < nsteps && rc == SPH_OK; ++s) rc = launch_step(ctx, cs, nullptr, &kernels);
+    cudaError_t e = cudaStreamEndCapture(cs, &g);
+    // capture advanced the host-side parity exactly as real steps do; rewind
+    ctx->parity = par;
+    bind_arrays(ctx);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(ctx, SPH_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(ctx, SPH_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+    *kernels_out = kernels;
+    return SPH_OK;
+}
+
 int sph_step(SphCtx *ctx, int32_t nsteps, void *stream) {
     if (!ctx || nsteps < 0) return SPH_E_ARG;
     if (ctx->P.n == 0) return SPH_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    for (int s = 0; s < nsteps; ++s) {
-        int par = ctx->parity;
-        if (!ctx->graph[par]) {
-            // capture one step starting from this ping-pong parity
-            cudaGraph_t g = nullptr;
-            int64_t kernels = 0;
-            if (!ctx->capture_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking));
-            cudaStream_t cs = ctx->capture_stream;
-            CUDA_TRY(ctx, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-            int rc = launch_step(ctx, cs, nullptr, &kernels);
-            cudaError_t e = cudaStreamEndCapture(cs, &g);
-            if (rc) { if (g) cudaGraphDestroy(g); ctx->parity = par; bind_arrays(ctx); return rc; }
-            if (e != cudaSuccess) { ctx->parity = par; bind_arrays(ctx); return fail(ctx, SPH_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e)); }
-            e = cudaGraphInstantiate(&ctx->graph[par], g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) { ctx->parity = par; bind_arrays(ctx); return fail(ctx, SPH_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
-            ctx->graph_kernels[par] = kernels;
-            // capture advanced the host-side parity exactly as a real step does; rewind and replay
-            ctx->parity = par;
-            bind_arrays(ctx);
+    int s = 0;
+    while (s < nsteps) {
+        const int par = ctx->parity;
+        // GRAPH_UNROLL (even) steps per replay amortise the graph-launch gap; the parity returns to `par`
+        const bool multi = nsteps - s >= GRAPH_UNROLL;
+        cudaGraphExec_t *slot = multi ? &ctx->graph_multi[par] : &ctx->graph[par];
+        int64_t *kslot = multi ? &ctx->graph_multi_kernels[par] : &ctx->graph_kernels[par];
+        const int span = multi ? GRAPH_UNROLL : 1;
+        if (!*slot) {
+            int rc = capture_steps(ctx, span, slot, kslot);
+            if (rc) return rc;
         }
-        CUDA_TRY(ctx, cudaGraphLaunch(ctx->graph[par], st));
-        ctx->launches += ctx->graph_kernels[par];
-        ctx->parity = par ^ 1;
-        bind_arrays(ctx);
+        CUDA_TRY(ctx, cudaGraphLaunch(*slot, st));
+        ctx->launches += *kslot;
+        if (span & 1) { ctx->parity = par ^ 1; bind_arrays(ctx); }
         ctx->built = false;
+        s += span;
     }
     return SPH_OK;
 }

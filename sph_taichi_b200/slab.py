@@ -320,6 +320,43 @@ def bench_main(args):
     mx = owned.clone()
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler else None
+
+    # ---- e2e: every step, H2D of the live records' {x, m_V} and {v, rho} words from pinned host
+    # memory, the sharded step, and D2H of the same words (what a host-side consumer reads) ----
+    Ke = max(3, min(K, 50))
+    cap = sim.b.n_max
+    h_pos = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
+    h_vel = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
+
+    def pull():
+        sim._await_info()
+        n_live = int(sim.info_all[rank][0])
+        v = sim.b.record_views()
+        h_pos[:n_live].copy_(v[0][:n_live], non_blocking=True)
+        h_vel[:n_live].copy_(v[1][:n_live], non_blocking=True)
+        return n_live
+
+    def push(n_live):
+        v = sim.b.record_views()
+        v[0][:n_live].copy_(h_pos[:n_live], non_blocking=True)
+        v[1][:n_live].copy_(h_vel[:n_live], non_blocking=True)
+
+    n_live = pull()
+    torch.cuda.synchronize()
+    dist.barrier()
+    moved = 0
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        push(n_live)
+        sim.step()
+        moved += 32 * n_live
+        n_live = pull()
+        moved += 32 * n_live
+        torch.cuda.current_stream().synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    moved_t = torch.tensor([float(moved)], device=dev, dtype=torch.float64)
+    dist.all_reduce(moved_t, op=dist.ReduceOp.SUM)
     if rank == 0:
         t_ms = float(ms.item())
         val = K / (t_ms * 1e-3)
@@ -336,8 +373,14 @@ def bench_main(args):
             "halo": {"bytes_per_step_all_ranks": halo_per_step,
                      "fraction_of_owned_state": halo_per_step / (64.0 * max(tot[0].item(), 1.0))},
             "clocks": clocks,
-            "e2e": None, "gpu_launches": int(tot[2].item()),
+            "e2e": {"value": Ke / float(e2e_s.item()) * n_total / 1e6, "unit": _bench.UNIT,
+                    "steps_per_s": Ke / float(e2e_s.item()), "steps": Ke,
+                    "h2d_bytes_per_step": int(moved_t.item() / (2 * Ke)), "d2h_bytes_per_step": int(moved_t.item() / (2 * Ke)),
+                    "note": "per rank and step: pinned-host -> device copy of the live records' position and velocity "
+                            "words, sharded step (NCCL halo exchange inside), device -> pinned-host copy back; max over ranks"},
+            "gpu_launches": int(tot[2].item()),
             "roofline": None, "cpu_baseline": None,
+            "notes": "roofline and cpu_baseline are reported by the N = 1 run (bench.py contract)",
         }
         print(json.dumps(line))
     dist.barrier()
