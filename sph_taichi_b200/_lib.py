@@ -19,7 +19,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 # every symbol include/sph_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
-    "sph_workspace_bytes", "sph_create", "sph_destroy", "sph_last_error", "sph_set_params", "sph_set_solid_count",
+    "sph_workspace_bytes", "sph_create", "sph_destroy", "sph_last_error", "sph_set_params", "sph_set_solid_count", "sph_set_fluid_uniform",
     "sph_pack", "sph_unpack", "sph_unpack_xv", "sph_upload_xv", "sph_copy_grid_particles_num", "sph_neighbor_build",
     "sph_boundary_volume", "sph_compute_densities", "sph_compute_non_pressure_forces", "sph_compute_pressure_forces",
     "sph_advect", "sph_enforce_boundary", "sph_set_rigid_bodies", "sph_compute_com", "sph_compute_rigid_rest_cm",
@@ -95,6 +95,7 @@ def load():
         "sph_last_error": (C.c_char_p, [vp]),
         "sph_set_params": (C.c_int, [vp, PP]),
         "sph_set_solid_count": (C.c_int, [vp, i64, i32]),
+        "sph_set_fluid_uniform": (C.c_int, [vp, i32, C.c_float, C.c_float]),
         "sph_pack": (C.c_int, [vp, FP, i64, vp]),
         "sph_unpack": (C.c_int, [vp, FP, vp]),
         "sph_unpack_xv": (C.c_int, [vp, vp, vp, vp, vp]),

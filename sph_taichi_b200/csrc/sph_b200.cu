@@ -25,7 +25,7 @@ enum { T_ZERO, T_HASH, T_SCAN, T_BUCKET, T_MOVE, T_BVOL, T_DENSITY, T_FORCE, T_A
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
-    uint64_t off_state[11];  // posm, veld, x0id, misc, acc (x2), aux
+    uint64_t off_state[13];  // posm, veld, x0id, misc, acc (x2), aux, fpos, fvel
     uint64_t off_cid, off_grid_ids, off_perm;
     uint64_t off_zero_begin, off_tile_counter, off_tile_state, off_cell_end, off_cell_fill, off_zero_end;
     uint64_t off_solid_slot, off_status, off_bodies, off_scratch, off_nbr_list, off_nbr_cnt;
@@ -39,7 +39,7 @@ Layout make_layout(int64_t n_max, int64_t C, int64_t n_solid, int n_bodies) {
     uint64_t o = 0;
     auto take = [&](uint64_t bytes) { uint64_t r = o; o = align_up(o + bytes, 256); return r; };
     uint64_t n = (uint64_t)(n_max > 0 ? n_max : 1);
-    for (int k = 0; k < 11; ++k) L.off_state[k] = take(n * sizeof(float4));
+    for (int k = 0; k < 13; ++k) L.off_state[k] = take(n * sizeof(float4));
     L.off_cid = take(n * 4);
     L.off_grid_ids = take(n * 4);
     L.off_perm = take(n * 4);
@@ -84,7 +84,7 @@ struct SphCtx {
     cudaGraphExec_t graph_multi[2] = {nullptr, nullptr};  // GRAPH_UNROLL steps per replay
     int64_t graph_multi_kernels[2] = {0, 0};
     int parity = 0;
-    int var_density = 7, var_force = 1;  // production kernels; SPH_DENSITY_VARIANT / SPH_FORCE_VARIANT select the ablation variants
+    int var_density = 7, var_force = 6;  // production kernels; SPH_DENSITY_VARIANT / SPH_FORCE_VARIANT select the ablation variants
     cudaStream_t capture_stream = nullptr;  // graphs are captured here (the legacy stream cannot capture)
     bool built = false;  // neighbour structure valid for current positions
 };
@@ -140,13 +140,15 @@ void bind_arrays(SphCtx *c) {
     char *w = c->ws;
     const Layout &L = c->L;
     DevArrays &S = c->S;
-    float4 *st[11];
-    for (int k = 0; k < 11; ++k) st[k] = reinterpret_cast<float4 *>(w + L.off_state[k]);
+    float4 *st[13];
+    for (int k = 0; k < 13; ++k) st[k] = reinterpret_cast<float4 *>(w + L.off_state[k]);
     int p = c->parity;
     S.posm = st[0 + 5 * p]; S.veld = st[1 + 5 * p]; S.x0id = st[2 + 5 * p]; S.misc = st[3 + 5 * p]; S.acc = st[4 + 5 * p];
     int q = 1 - p;
     S.posm_n = st[0 + 5 * q]; S.veld_n = st[1 + 5 * q]; S.x0id_n = st[2 + 5 * q]; S.misc_n = st[3 + 5 * q]; S.acc_n = st[4 + 5 * q];
     S.aux = st[10];
+    S.fpos = st[11];
+    S.fvel = st[12];
     S.cid = reinterpret_cast<int32_t *>(w + L.off_cid);
     S.grid_ids = reinterpret_cast<int32_t *>(w + L.off_grid_ids);
     S.perm = reinterpret_cast<int32_t *>(w + L.off_perm);
@@ -235,6 +237,9 @@ void launch_pair_force(SphCtx *c, cudaStream_t st) {
         case 4: k_force_list_b<8, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
         case 5: k_force_list_b<4, 256><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S); break;
         case 0: k_force_list<<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
+        case 6: if (P.uniform_fluid && c->var_density >= 7) { k_force_packed<4, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break; }
+        case 7: if (P.uniform_fluid && c->var_density >= 7) { k_force_packed<8, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break; }
+        case 8: if (P.uniform_fluid && c->var_density >= 7) { k_force_packed<4, 256><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S); break; }
         default: k_force_list_b<4, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
     }
 }
@@ -382,6 +387,15 @@ int sph_set_solid_count(SphCtx *ctx, int64_t n_solid, int32_t has_dynamic_solids
     if (n_solid < 0 || n_solid > ctx->n_solid_cap) return fail(ctx, SPH_E_CAPACITY, "n_solid exceeds the capacity given at creation");
     ctx->P.n_solid = (int32_t)n_solid;
     ctx->has_dynamic_solids = has_dynamic_solids != 0;
+    drop_graphs(ctx);
+    return SPH_OK;
+}
+
+int sph_set_fluid_uniform(SphCtx *ctx, int32_t uniform, float fluid_m, float fluid_mV) {
+    if (!ctx) return SPH_E_ARG;
+    ctx->P.uniform_fluid = uniform ? 1 : 0;
+    ctx->P.fluid_m = fluid_m;
+    ctx->P.fluid_mV = fluid_mV;
     drop_graphs(ctx);
     return SPH_OK;
 }

@@ -36,12 +36,20 @@ struct DevParams {
     // x-slab sharding (multi-GPU): this rank owns cell layers [sx0, sx1) and keeps sgw ghost
     // layers per side.  Records [n_local, n) were just received from the neighbour ranks.
     int32_t slab_on, sx0, sx1, sgw, n_local;
+    // all fluid particles share one mass and one volume (true for every scene the reference can
+    // express with a single fluid density): the force pass then needs only 2 x 16 B per neighbour
+    int32_t uniform_fluid;
+    float fluid_m, fluid_mV;
 };
 
 struct DevArrays {
     float4 *posm, *veld, *x0id, *misc, *acc;       // current (sorted) state
     float4 *posm_n, *veld_n, *x0id_n, *misc_n, *acc_n;  // sort destination
     float4 *aux;
+    // per-step packed neighbour data of the uniform-fluid force pass (written by the density pass):
+    //   fpos = {x, y, z, fluid: m/rho_unclamped | solid: m_V}
+    //   fvel = {vx, vy, vz, fluid: p/rho^2 (>= 0) | solid: -body density (dynamic) or -inf (static)}
+    float4 *fpos, *fvel;
     int32_t *cid;       // cell id per particle in pre-sort order
     int32_t *grid_ids;  // cell id per particle in sorted order (public grid_ids)
     int32_t *perm;      // bucket slot -> pre-sort index

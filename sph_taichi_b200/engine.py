@@ -104,6 +104,15 @@ class Engine:
     def pack(self, tensors, n, n_solid, has_dynamic_solids):
         self._check(self.lib.sph_set_solid_count(self.ctx, int(n_solid), int(bool(has_dynamic_solids))),
                     "sph_set_solid_count")
+        # uniform-fluid hint: all fluid particles share one m and one m_V (bitwise)
+        uniform, fm, fmv = 0, 0.0, 0.0
+        if n > 0:
+            fluid = tensors["material"][:n] == 1
+            if bool(fluid.any().item()):
+                m, mv = tensors["m"][:n][fluid], tensors["m_V"][:n][fluid]
+                fm, fmv = float(m[0].item()), float(mv[0].item())
+                uniform = int(bool((m == m[0]).all().item()) and bool((mv == mv[0]).all().item()))
+        self._check(self.lib.sph_set_fluid_uniform(self.ctx, uniform, fm, fmv), "sph_set_fluid_uniform")
         f = self.fields_struct(tensors)
         self._check(self.lib.sph_pack(self.ctx, C.byref(f), int(n), self._stream()), "sph_pack")
 

@@ -305,7 +305,12 @@ def test_slab_two_gpus_equals_single_gpu():
 
 def test_armadillo_bath_dynamic_full_size():
     """BASELINE cfg 3 (1.74 M particles, three dynamic rigid bodies): a few real steps against the
-    oracle, plus size-independent properties (rigidity of the shape-matched bodies, sortedness)."""
+    oracle, plus size-independent properties (rigidity of the shape-matched bodies, sortedness).
+
+    The centre of mass of a body is an fp32 sum of 5490 same-sign terms; the oracle adds them
+    serially (biased rounding, ~1e-4 m), the reference with unordered atomics, the engine with a
+    fixed tree.  So the rigid particles are judged against the fp64 oracle, with the fp32 oracle's
+    own distance to it as the noise floor."""
     from oracle.sph_oracle import OracleSim
     from sph_taichi_b200 import ParticleSystem, SimConfig, scene
     sc = scene.armadillo_bath_dynamic()
@@ -313,21 +318,29 @@ def test_armadillo_bath_dynamic_full_size():
     assert ps.fluid_particle_num == 1723968 and ps.solid_particle_num == 3 * 5490
     solver = ps.build_solver()
     solver.initialize()
-    o = OracleSim(sc)
-    o.initialize()
-    for oid in (1, 2, 3):  # fp32 sums of 5490 terms: tree order (engine) vs serial order (oracle)
-        assert _maxrel(ps.rigid_rest_cm[oid], o.rest_cm[oid]) < 1e-4
+    o, o64 = OracleSim(sc), OracleSim(sc, f64=True)
+    o.initialize(); o64.initialize()
+    for oid in (1, 2, 3):
+        assert _maxrel(ps.rigid_rest_cm[oid], o64.rest_cm[oid]) < 1e-6
     steps = 6
     solver.step(steps)
     for _ in range(steps):
-        o.step()
+        o.step(); o64.step()
     assert ps._engine.check_status() == 0
     x, x0, oid_g = ps.x.to_numpy(), ps.x_0.to_numpy(), ps.object_id.to_numpy()
-    kg, ko = order_by_x0(x0), order_by_x0(o.x_0)
     # rigid bodies share rest lattices (shifted copies), so key on (object id, x_0)
-    kg = np.lexsort((x0[:, 2], x0[:, 1], x0[:, 0], oid_g)); ko = np.lexsort((o.x_0[:, 2], o.x_0[:, 1], o.x_0[:, 0], o.object_id))
+    kg = np.lexsort((x0[:, 2], x0[:, 1], x0[:, 0], oid_g))
+    ko = np.lexsort((o.x_0[:, 2], o.x_0[:, 1], o.x_0[:, 0], o.object_id))
+    x064 = o64.x_0.astype(np.float32)
+    k64 = np.lexsort((x064[:, 2], x064[:, 1], x064[:, 0], o64.object_id))
     assert np.array_equal(x0[kg], o.x_0[ko]) and np.array_equal(oid_g[kg], o.object_id[ko])
-    assert np.abs(x[kg] - o.x[ko]).max() / 0.02 < 1e-3
+    assert np.array_equal(x0[kg], x064[k64])
+    fluid = oid_g[kg] == 0
+    d = 0.02
+    assert np.abs(x[kg] - o.x[ko])[fluid].max() / d < 1e-3
+    err_rigid = np.abs(x[kg] - o64.x[k64])[~fluid].max() / d
+    floor_rigid = np.abs(o.x[ko] - o64.x[k64])[~fluid].max() / d
+    assert err_rigid < max(3 * floor_rigid, 1e-3), (err_rigid, floor_rigid)
     assert _maxrel(ps.v.to_numpy()[kg], o.v[ko]) < 1e-3
     assert np.all(np.diff(ps.grid_ids.to_numpy()) >= 0)
     for b in (1, 2, 3):  # shape matching keeps every body congruent to its rest shape

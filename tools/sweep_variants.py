@@ -8,9 +8,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scene", default="dragon_bath")
 ap.add_argument("--dv", type=int, nargs="*", default=[0, 1, 2, 3, 4, 5])
 ap.add_argument("--fv", type=int, nargs="*", default=[0, 1, 2, 3, 4, 5])
+ap.add_argument("--pairs", type=str, default="", help="explicit dv:fv pairs, comma separated")
 ap.add_argument("--warm", type=int, default=100)
 a = ap.parse_args()
 combos = [(d, 0) for d in a.dv] + [(0, f) for f in a.fv if f != 0]
+if a.pairs:
+    combos = [tuple(int(v) for v in p.split(":")) for p in a.pairs.split(",")]
 for dv, fv in combos:
     os.environ["SPH_DENSITY_VARIANT"] = str(dv)
     os.environ["SPH_FORCE_VARIANT"] = str(fv)
