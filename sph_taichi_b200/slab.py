@@ -116,12 +116,16 @@ class EngineBackend:
         """The 4 exchanged packed arrays as [n_max, 4] float32 views of the engine workspace."""
         off = (C.c_uint64 * 5)()
         self.eng._check(self.eng.lib.sph_state_offsets(self.eng.ctx, off), "sph_state_offsets")
-        base = self.eng._ws_ptr - self.eng.workspace.data_ptr()
-        views = []
-        for k in range(RECORD_ARRAYS):
-            b0 = base + int(off[k])
-            views.append(self.eng.workspace[b0:b0 + self.n_max * 16].view(torch.float32).view(self.n_max, 4))
-        return views
+        key = int(off[0])
+        cache = self.__dict__.setdefault("_view_cache", {})
+        if key not in cache:  # two entries: the ping-pong buffer sets
+            base = self.eng._ws_ptr - self.eng.workspace.data_ptr()
+            views = []
+            for k in range(RECORD_ARRAYS):
+                b0 = base + int(off[k])
+                views.append(self.eng.workspace[b0:b0 + self.n_max * 16].view(torch.float32).view(self.n_max, 4))
+            cache[key] = views
+        return cache[key]
 
     def sort(self, n_local, n_recv):
         e = self.eng
@@ -166,20 +170,34 @@ class SlabSimulation:
 
     # -- helpers ---------------------------------------------------------------------------
     def _gather_info(self, info_dev):
-        """all_gather the info rows; the host copy is awaited lazily at the next step."""
-        if self.world == 1:
-            gathered = info_dev.clone().view(1, 8)
-        else:
-            gathered = torch.empty((self.world, 8), dtype=info_dev.dtype, device=info_dev.device)
-            dist.all_gather_into_tensor(gathered.view(-1), info_dev, group=self.group)
-        if gathered.is_cuda:
-            host = torch.empty((self.world, 8), dtype=gathered.dtype).pin_memory()
-            host.copy_(gathered, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            self._pending = (host, ev, gathered)
-        else:
+        """all_gather the info rows; the host copy is awaited lazily at the next step.  On the GPU
+        the collective and the D2H copy run on a side stream so the pair kernels start immediately."""
+        if not info_dev.is_cuda:
+            if self.world == 1:
+                gathered = info_dev.clone().view(1, 8)
+            else:
+                gathered = torch.empty((self.world, 8), dtype=info_dev.dtype)
+                dist.all_gather_into_tensor(gathered.view(-1), info_dev, group=self.group)
             self._pending = (gathered, None, None)
+            return
+        if not hasattr(self, "_pinned"):
+            self._pinned = [torch.empty((self.world, 8), dtype=info_dev.dtype).pin_memory() for _ in range(2)]
+            self._gathered = [torch.empty((self.world, 8), dtype=info_dev.dtype, device=info_dev.device) for _ in range(2)]
+            self._events = [torch.cuda.Event() for _ in range(2)]
+            self._side = torch.cuda.Stream(device=info_dev.device)
+            self._flip = 0
+        self._flip ^= 1
+        host, ev, gathered = self._pinned[self._flip], self._events[self._flip], self._gathered[self._flip]
+        main = torch.cuda.current_stream(info_dev.device)
+        self._side.wait_stream(main)  # the info kernel has run
+        with torch.cuda.stream(self._side):
+            if self.world == 1:
+                gathered.view(-1).copy_(info_dev)
+            else:
+                dist.all_gather_into_tensor(gathered.view(-1), info_dev, group=self.group)
+            host.copy_(gathered, non_blocking=True)
+            ev.record(self._side)
+        self._pending = (host, ev, gathered)
 
     def _await_info(self):
         host, ev, _ = self._pending
@@ -196,7 +214,10 @@ class SlabSimulation:
         self._gather_info(info)
 
     def step(self):
+        prof = self.__dict__.setdefault("_prof", [0.0] * 6) if os.environ.get("SPH_SLAB_PROF") else None
+        t0 = time.perf_counter()
         self._await_info()
+        t1 = time.perf_counter()
         me = self.info_all[self.rank]
         n_live = int(me[0])
         left, right = self.rank - 1, self.rank + 1
@@ -221,14 +242,42 @@ class SlabSimulation:
                     ops.append(dist.P2POp(dist.isend, arr[sr0:sr1], right, self.group))
                 if n_from_right:
                     ops.append(dist.P2POp(dist.irecv, arr[a1:a1 + n_from_right], right, self.group))
+        t2 = time.perf_counter()
+        gp = None
+        if prof is not None:
+            gp = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            gp[0].record()
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
+        t3 = time.perf_counter()
+        if gp: gp[1].record()
         self.halo_bytes += 16 * RECORD_ARRAYS * (n_from_left + n_from_right)
         info = self.b.sort(n_live, n_from_left + n_from_right)
+        t4 = time.perf_counter()
+        if gp: gp[2].record()
         self._gather_info(info)
+        t5 = time.perf_counter()
+        if gp: gp[3].record()
         self.b.compute()
+        if gp:
+            gp[4].record()
+            self.__dict__.setdefault("_gpu_ev", []).append(gp)
         self.steps_done += 1
+        if prof is not None:
+            t6 = time.perf_counter()
+            for k, dt in enumerate((t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t6 - t5)):
+                prof[k] += dt
+            if self.steps_done % 50 == 0:
+                names = ("await_info", "build_ops", "nccl_p2p", "sort_launch", "gather_info", "compute_launch")
+                print("[slab host us/step] " + " ".join(f"{n}={v / self.steps_done * 1e6:.0f}" for n, v in zip(names, prof)),
+                      flush=True)
+                torch.cuda.synchronize()
+                evs = self._gpu_ev[-40:]
+                seg = [sum(e[k].elapsed_time(e[k + 1]) for e in evs) / len(evs) * 1e3 for k in range(4)]
+                print(f"[rank {self.rank}] " "[slab gpu us/step] exchange=%.0f sort=%.0f gather_info=%.0f compute=%.0f n_live=%d recv=%d" % (
+                    *seg, n_live, n_from_left + n_from_right), flush=True)
+                self._gpu_ev.clear()
 
     def owned_state(self):
         self._await_info()
