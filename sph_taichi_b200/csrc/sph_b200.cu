@@ -84,7 +84,7 @@ struct SphCtx {
     cudaGraphExec_t graph_multi[2] = {nullptr, nullptr};  // GRAPH_UNROLL steps per replay
     int64_t graph_multi_kernels[2] = {0, 0};
     int parity = 0;
-    int var_density = 7, var_force = 6;  // production kernels; SPH_DENSITY_VARIANT / SPH_FORCE_VARIANT select the ablation variants
+    int var_density = 1, var_force = 1;  // 1 = production; 0 = ablation variants (SPH_DENSITY_VARIANT / SPH_FORCE_VARIANT)
     cudaStream_t capture_stream = nullptr;  // graphs are captured here (the legacy stream cannot capture)
     bool built = false;  // neighbour structure valid for current positions
 };
@@ -164,7 +164,6 @@ void bind_arrays(SphCtx *c) {
 }
 
 inline RigidBodyDev *dev_bodies(SphCtx *c) { return reinterpret_cast<RigidBodyDev *>(c->ws + c->L.off_bodies); }
-inline float *dev_scratch(SphCtx *c) { return reinterpret_cast<float *>(c->ws + c->L.off_scratch); }
 
 inline int blocks_for(int64_t n, int t) { return (int)((n + t - 1) / t); }
 
@@ -214,34 +213,32 @@ int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *k
     return SPH_OK;
 }
 
-void launch_pair_density(SphCtx *c, cudaStream_t st) {
+// density + neighbour lists, then forces (+ integration).  SPH_DENSITY_VARIANT / SPH_FORCE_VARIANT = 0
+// select the ablation variants (second dense loop for the density sum; separate advect kernel).
+void launch_pair_density(SphCtx *c, cudaStream_t st, int64_t *kernels) {
     const DevParams &P = c->P;
-    switch (c->var_density) {
-        case 1: k_density_list_b<4, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
-        case 2: k_density_list_b<4, 64><<<blocks_for(P.n, 64), 64, 0, st>>>(P, c->S); break;
-        case 3: k_density_list_b<2, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
-        case 4: k_density_list_b<8, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
-        case 5: k_density_list_b<4, 256><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S); break;
-        case 7: k_density_tma2<<<blocks_for(P.n, DENS_WARPS * 32), DENS_WARPS * 32, 0, st>>>(P, c->S); break;
-        case 6: k_density_tma<<<blocks_for(P.n, DENS_WARPS * 32), DENS_WARPS * 32, 0, st>>>(P, c->S); break;
-        case 0: k_density_list<true><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
-        default: k_density_tma2<<<blocks_for(P.n, DENS_WARPS * 32), DENS_WARPS * 32, 0, st>>>(P, c->S); break;
-    }
+    const int blocks = blocks_for(P.n, DENS_WARPS * 32);
+    if (c->var_density == 0) k_density_tma<false><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
+    else k_density_tma<true><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
+    *kernels += 1;
 }
-void launch_pair_force(SphCtx *c, cudaStream_t st) {
+void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels) {
     const DevParams &P = c->P;
-    switch (c->var_force) {
-        case 1: k_force_list_b<4, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
-        case 2: k_force_list_b<4, 64><<<blocks_for(P.n, 64), 64, 0, st>>>(P, c->S); break;
-        case 3: k_force_list_b<2, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
-        case 4: k_force_list_b<8, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
-        case 5: k_force_list_b<4, 256><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S); break;
-        case 0: k_force_list<<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
-        case 6: if (P.uniform_fluid && c->var_density >= 7) { k_force_packed<4, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break; }
-        case 7: if (P.uniform_fluid && c->var_density >= 7) { k_force_packed<8, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break; }
-        case 8: if (P.uniform_fluid && c->var_density >= 7) { k_force_packed<4, 256><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S); break; }
-        default: k_force_list_b<4, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S); break;
+    if (P.uniform_fluid && c->var_force != 0) {
+        k_force_packed<4, 128, true><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
+        *kernels += 1;
+        if (tm) tm->mark(T_ADVECT);
+        if (c->has_dynamic_solids && P.n_solid > 0) {
+            k_advect_solids<<<blocks_for(P.n_solid, 256), 256, 0, st>>>(P, c->S);
+            *kernels += 1;
+        }
+        return;
     }
+    if (P.uniform_fluid) k_force_packed<4, 128, false><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
+    else k_force_general<4, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
+    if (tm) tm->mark(T_ADVECT);
+    k_advect<true><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
+    *kernels += 2;
 }
 
 int launch_boundary_volume(SphCtx *c, int moving, cudaStream_t st, int64_t *kernels) {
@@ -273,12 +270,9 @@ int launch_step(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels) {
     if (tm) tm->mark(T_BVOL);
     if (c->has_dynamic_solids) { rc = launch_boundary_volume(c, 1, st, kernels); if (rc) return rc; }
     if (tm) tm->mark(T_DENSITY);
-    launch_pair_density(c, st);
+    launch_pair_density(c, st, kernels);
     if (tm) tm->mark(T_FORCE);
-    launch_pair_force(c, st);
-    if (tm) tm->mark(T_ADVECT);
-    k_advect<true><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
-    *kernels += 3;
+    launch_pair_force_and_advect(c, st, tm, kernels);
     if (tm) tm->mark(T_RIGID);
     if (!c->bodies.empty()) { rc = launch_rigid_solve(c, st, kernels); if (rc) return rc; }
     if (tm) tm->mark(T_TOTAL);
@@ -454,7 +448,7 @@ int sph_boundary_volume(SphCtx *ctx, int32_t moving, void *stream) {
 
 int sph_compute_densities(SphCtx *ctx, void *stream) {
     REQUIRE_BUILT(ctx);
-    k_density<false><<<blocks_for(ctx->P.n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S);
+    k_density_simple<false><<<blocks_for(ctx->P.n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S);
     ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());
     return SPH_OK;
@@ -462,7 +456,7 @@ int sph_compute_densities(SphCtx *ctx, void *stream) {
 
 int sph_compute_non_pressure_forces(SphCtx *ctx, void *stream) {
     REQUIRE_BUILT(ctx);
-    k_force<true, false><<<blocks_for(ctx->P.n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S);
+    k_force_simple<true, false><<<blocks_for(ctx->P.n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S);
     ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());
     return SPH_OK;
@@ -472,7 +466,7 @@ int sph_compute_pressure_forces(SphCtx *ctx, void *stream) {
     REQUIRE_BUILT(ctx);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     k_eos<<<blocks_for(ctx->P.n, 256), 256, 0, st>>>(ctx->P, ctx->S);
-    k_force<false, true><<<blocks_for(ctx->P.n, 128), 128, 0, st>>>(ctx->P, ctx->S);
+    k_force_simple<false, true><<<blocks_for(ctx->P.n, 128), 128, 0, st>>>(ctx->P, ctx->S);
     ctx->launches += 2;
     CUDA_TRY(ctx, cudaGetLastError());
     return SPH_OK;
@@ -640,10 +634,8 @@ int sph_slab_compute(SphCtx *ctx, void *stream) {
     if (P.n == 0) return SPH_OK;
     if (!ctx->built) return fail(ctx, SPH_E_ARG, "sph_slab_compute needs a fresh sph_slab_step(sort_only = 1)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    launch_pair_density(ctx, st);
-    launch_pair_force(ctx, st);
-    k_advect<true><<<blocks_for(P.n, 256), 256, 0, st>>>(P, ctx->S);
-    ctx->launches += 3;
+    launch_pair_density(ctx, st, &ctx->launches);
+    launch_pair_force_and_advect(ctx, st, nullptr, &ctx->launches);
     ctx->built = false;
     CUDA_TRY(ctx, cudaGetLastError());
     return SPH_OK;

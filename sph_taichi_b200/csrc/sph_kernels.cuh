@@ -271,7 +271,8 @@ __global__ void k_rank_move(DevParams P, DevArrays S) {
 }
 
 // =====================================================================================
-// pair kernels (v1: one thread per particle, neighbours gathered through L1)
+// simple pair kernels (v1): one thread per particle, 27-cell walk through L1.  They back the
+// reference-named un-fused entry points and are the fallback for over-full neighbour lists.
 // =====================================================================================
 
 // Akinci boundary volumes (sph_base.py:91-113).  One thread per SOLID particle.
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(128) k_boundary_volume(DevParams P, DevArrays 
 // WCSPH.py:73-76 and initialises the accelerations of non-fluid particles (WCSPH.py:130-137),
 // so the fused force pass can follow immediately.
 template <bool FUSE_EOS>
-__global__ void __launch_bounds__(128) k_density(DevParams P, DevArrays S) {
+__global__ void __launch_bounds__(128) k_density_simple(DevParams P, DevArrays S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     float4 pi = S.posm[i];
@@ -346,7 +347,7 @@ __global__ void k_eos(DevParams P, DevArrays S) {
 // Forces.  NP: compute_non_pressure_forces (WCSPH.py:88-140); PR: the gather loop of
 // compute_pressure_forces (WCSPH.py:46-68,77-85).  NP && PR is the fused production pass.
 template <bool NP, bool PR>
-__global__ void __launch_bounds__(128) k_force(DevParams P, DevArrays S) {
+__global__ void __launch_bounds__(128) k_force_simple(DevParams P, DevArrays S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     float4 mi = S.misc[i];
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(128) k_force(DevParams P, DevArrays S) {
         bool dyn = (fl & FLAG_DYNAMIC) != 0;
         if (NP && !PR) S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (PR && !NP && !dyn) S.acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;  // fused: initialised by k_density<true>
+        return;  // fused: initialised by the density pass
     }
     float4 pi = S.posm[i];
     float4 vi = S.veld[i];
@@ -598,111 +599,30 @@ __global__ void __launch_bounds__(RIGID_THREADS) k_rigid(DevParams P, DevArrays 
 }
 
 // =====================================================================================
-// pair kernels v2: per-step neighbour lists.
+// Production pair kernels.  History and measurements: DESIGN.md section 3.1, profiles/.
 //
-// ncu on v1 (profiles/r01_v1_*.txt): both pair kernels are instruction-issue bound (66-75 % issue
-// active) and the force pass retires only ~16 of 32 lanes per instruction, because the expensive
-// hit path runs under a ~15 % per-lane hit rate.  v2 separates the two regimes:
-//   density pass = candidate scan (cheap body: distance test + list append) followed by a dense
-//                  loop over the compacted list;
-//   force pass   = dense loop over the same list, no candidate scan at all.
-// The list keeps the reference's visiting order, so sums are accumulated in the oracle's order.
-// Particles with more than NBR_CAP neighbours (never in the shipped scenes) fall back to the
-// v1 full scan inside the same kernels.
+//  * The density pass scans the 27-cell candidates once per step and appends the accepted pairs
+//    to a per-particle neighbour list (reference visiting order); the force pass is a dense loop
+//    over that list (v1 executed the 80-instruction hit path under a ~15 % per-lane hit rate).
+//  * Candidate windows are staged by TMA: each WARP copies, per (dx, dy) column, the union of its
+//    lanes' candidate ranges -- one contiguous run of the sorted posm array -- into shared memory
+//    with one cp.async.bulk (SASS UBLKCP) completing on an mbarrier, double-buffered over the 9
+//    columns; lanes scan their own sub-range with LDS.128.
+//  * The scan is branch-free: 32 candidates at a time into a per-lane hit bitmask, then the set
+//    bits are flushed (list append + density contribution straight from the staged window).
+//  * The force pass gathers 2 x 16 B per neighbour (uniform fluids) in batches of 4 with all
+//    loads of a batch issued before any arithmetic, and integrates the particle in its epilogue.
+//  Particles with more than NBR_CAP neighbours fall back to the v1 full scan in the same kernels.
 // =====================================================================================
-template <bool FUSE_EOS>
-__global__ void __launch_bounds__(128) k_density_list(DevParams P, DevArrays S) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
-    if (P.slab_on && S.grid_ids[i] >= P.C) return;  // trash bucket
-    float4 pi = S.posm[i];
-    float4 mi = S.misc[i];
-    uint32_t fl = __float_as_uint(mi.z);
-    if (!(fl & FLAG_FLUID)) {
-        bool dyn = (fl & FLAG_DYNAMIC) != 0;
-        S.aux[i] = make_float4(S.veld[i].w, 0.0f, dyn ? -2.0f : -1.0f, 0.0f);
-        if (FUSE_EOS) S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
-        S.nbr_cnt[i] = 0;
-        return;
-    }
-    // ---- phase 1: candidate scan, append hits ----
-    int cnt = 0;
-    {
-        int32_t *lp = S.nbr_list + i;
-        const size_t stride = (size_t)S.npad;
-        int ci, cj, ck;
-        cell_of(P, pi.x, pi.y, pi.z, ci, cj, ck);
-        ci = min(max(ci, 0), P.gx - 1); cj = min(max(cj, 0), P.gy - 1); ck = min(max(ck, 0), P.gz - 1);
-        int k_lo = max(ck - 1, 0), k_hi = min(ck + 1, P.gz - 1);
-        for (int dx = -1; dx <= 1; ++dx) {
-            int ni = ci + dx;
-            if (ni < 0 || ni >= P.gx) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                int nj = cj + dy;
-                if (nj < 0 || nj >= P.gy) continue;
-                int row = (ni * P.gy + nj) * P.gz;
-                int j0 = __ldg(S.cell_end + max(row + k_lo - 1, 0));
-                int j1 = __ldg(S.cell_end + row + k_hi);
-#pragma unroll 4
-                for (int j = j0; j < j1; ++j) {
-                    float4 pj = __ldg(S.posm + j);
-                    float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-                    float r2 = rx * rx + ry * ry + rz * rz;
-                    if (r2 < P.h2 && j != i) {
-                        if (cnt < NBR_CAP) { *lp = j; lp += stride; }
-                        ++cnt;
-                    }
-                }
-            }
-        }
-    }
-    float den = 0.0f;
-    if (cnt <= NBR_CAP) {
-        S.nbr_cnt[i] = cnt;
-        // ---- phase 2: dense loop over the list ----
-        const int32_t *lp = S.nbr_list + i;
-        const size_t stride = (size_t)S.npad;
-        for (int k = 0; k < cnt; ++k) {
-            int j = *lp; lp += stride;
-            float4 pj = __ldg(S.posm + j);
-            float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-            float r2 = rx * rx + ry * ry + rz * rz;
-            float r, inv_r;
-            fast_norm(r2, r, inv_r);
-            den += pj.w * w_cubic(P, r);
-        }
-    } else {
-        S.nbr_cnt[i] = NBR_OVERFLOW;
-        for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
-                          [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
-                              den += pj.w * w_cubic(P, sqrtf(r2));
-                          });
-    }
-    float rho = pi.w * P.w0;
-    rho += den;
-    rho *= P.rho0;
-    float vol = mi.x / rho;
-    if (FUSE_EOS) {
-        float rc = fmaxf(rho, P.rho0);
-        float p = tait_pressure(P, rc);
-        reinterpret_cast<float *>(S.veld + i)[3] = rc;
-        reinterpret_cast<float *>(S.misc + i)[1] = p;
-        S.aux[i] = make_float4(vol, p / (rc * rc), mi.x, 0.0f);
-    } else {
-        reinterpret_cast<float *>(S.veld + i)[3] = rho;
-        S.aux[i] = make_float4(vol, 0.0f, mi.x, 0.0f);
-    }
-}
-
 struct ForceAcc {
     float npx, npy, npz, prx, pry, prz;
 };
 
-// one accepted pair of the fused force pass (WCSPH.py:46-68 and 88-125)
-__device__ __forceinline__ void force_pair(const DevParams &P, const DevArrays &S, ForceAcc &A, int j, float rx,
-                                           float ry, float rz, float r2, float mVj, const float4 &vi, float dpi,
-                                           float dpi_solid, float coh_i) {
-    float4 aj = __ldg(S.aux + j);
+// one accepted pair of the fused force pass (WCSPH.py:46-68 and 88-125); aj / vj already loaded
+__device__ __forceinline__ void force_pair_pre(const DevParams &P, const DevArrays &S, ForceAcc &A, int j, float rx,
+                                               float ry, float rz, float r2, float mVj, const float4 &aj,
+                                               const float4 &vj, const float4 &vi, float dpi, float dpi_solid,
+                                               float coh_i) {
     float r, inv_r;
     fast_norm(r2, r, inv_r);
     float gs = gradw_scale_fast(P, r, inv_r);
@@ -710,7 +630,6 @@ __device__ __forceinline__ void force_pair(const DevParams &P, const DevArrays &
         float w = (r2 > P.d2) ? w_cubic(P, r) : P.w_diam;
         float c = coh_i * aj.z;
         A.npx -= c * rx * w; A.npy -= c * ry * w; A.npz -= c * rz * w;
-        float4 vj = __ldg(S.veld + j);
         float vxy = (vi.x - vj.x) * rx + (vi.y - vj.y) * ry + (vi.z - vj.z) * rz;
         float sv = __fdividef(P.d_visc * aj.x * vxy, r * r + P.visc_eps) * gs;
         A.npx += sv * rx; A.npy += sv * ry; A.npz += sv * rz;
@@ -729,232 +648,11 @@ __device__ __forceinline__ void force_pair(const DevParams &P, const DevArrays &
     }
 }
 
-__global__ void __launch_bounds__(128) k_force_list(DevParams P, DevArrays S) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
-    if (P.slab_on && S.grid_ids[i] >= P.C) return;
-    float4 mi = S.misc[i];
-    uint32_t fl = __float_as_uint(mi.z);
-    if (!(fl & FLAG_FLUID)) return;  // initialised by k_density_list<true>
-    if (fl & FLAG_GHOST) return;     // ghosts are neighbours only
-    float4 pi = S.posm[i];
-    float4 vi = S.veld[i];
-    float4 ai = S.aux[i];
-    const float dpi = ai.y;
-    const float dpi_solid = dpi + mi.y * P.inv_rho0sq;
-    const float coh_i = P.sigma / mi.x;
-    ForceAcc A = {P.gx_, P.gy_, P.gz_, 0.f, 0.f, 0.f};
-    const int cnt = S.nbr_cnt[i];
-    if (cnt != NBR_OVERFLOW) {
-        const int32_t *lp = S.nbr_list + i;
-        const size_t stride = (size_t)S.npad;
-#pragma unroll 2
-        for (int k = 0; k < cnt; ++k) {
-            int j = *lp; lp += stride;
-            float4 pj = __ldg(S.posm + j);
-            float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-            float r2 = rx * rx + ry * ry + rz * rz;
-            force_pair(P, S, A, j, rx, ry, rz, r2, pj.w, vi, dpi, dpi_solid, coh_i);
-        }
-    } else {
-        for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
-                          [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
-                              force_pair(P, S, A, j, rx, ry, rz, r2, pj.w, vi, dpi, dpi_solid, coh_i);
-                          });
-    }
-    S.acc[i] = make_float4(A.npx + A.prx, A.npy + A.pry, A.npz + A.prz, 0.f);
-}
-
-// =====================================================================================
-// pair kernels v2b: the dense list loops in batches of B neighbours with all gathers of a batch
-// issued before any arithmetic (ncu on v2: both list loops stall on long_scoreboard, i.e. they are
-// latency-bound on the dependent list -> gather chain).  Tails are padded with the particle
-// itself, whose pair terms are exactly zero.
-// =====================================================================================
-__device__ __forceinline__ void force_pair_pre(const DevParams &P, const DevArrays &S, ForceAcc &A, int j, float rx,
-                                               float ry, float rz, float r2, float mVj, const float4 &aj,
-                                               const float4 &vj, const float4 &vi, float dpi, float dpi_solid,
-                                               float coh_i) {
-    float r, inv_r;
-    fast_norm(r2, r, inv_r);
-    float gs = gradw_scale_fast(P, r, inv_r);
-    if (aj.z > 0.0f) {
-        float w = (r2 > P.d2) ? w_cubic(P, r) : P.w_diam;
-        float c = coh_i * aj.z;
-        A.npx -= c * rx * w; A.npy -= c * ry * w; A.npz -= c * rz * w;
-        float vxy = (vi.x - vj.x) * rx + (vi.y - vj.y) * ry + (vi.z - vj.z) * rz;
-        float sv = __fdividef(P.d_visc * aj.x * vxy, r * r + P.visc_eps) * gs;
-        A.npx += sv * rx; A.npy += sv * ry; A.npz += sv * rz;
-        float cp = -P.rho0 * mVj * (dpi + aj.y) * gs;
-        A.prx += cp * rx; A.pry += cp * ry; A.prz += cp * rz;
-    } else {
-        float cp = -P.rho0 * mVj * dpi_solid * gs;
-        float fx = cp * rx, fy = cp * ry, fz = cp * rz;
-        A.prx += fx; A.pry += fy; A.prz += fz;
-        if (aj.z < -1.5f) {
-            float *a = reinterpret_cast<float *>(S.acc + j);
-            atomicAdd(a + 0, -fx * P.rho0 / aj.x);
-            atomicAdd(a + 1, -fy * P.rho0 / aj.x);
-            atomicAdd(a + 2, -fz * P.rho0 / aj.x);
-        }
-    }
-}
-
-template <int B, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_force_list_b(DevParams P, DevArrays S) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
-    if (P.slab_on && S.grid_ids[i] >= P.C) return;
-    float4 mi = S.misc[i];
-    uint32_t fl = __float_as_uint(mi.z);
-    if (!(fl & FLAG_FLUID)) return;
-    if (fl & FLAG_GHOST) return;
-    float4 pi = S.posm[i];
-    float4 vi = S.veld[i];
-    float4 ai = S.aux[i];
-    const float dpi = ai.y;
-    const float dpi_solid = dpi + mi.y * P.inv_rho0sq;
-    const float coh_i = P.sigma / mi.x;
-    ForceAcc A = {P.gx_, P.gy_, P.gz_, 0.f, 0.f, 0.f};
-    const int cnt = S.nbr_cnt[i];
-    if (cnt != NBR_OVERFLOW) {
-        const int32_t *lp = S.nbr_list + i;
-        const size_t stride = (size_t)S.npad;
-        for (int k0 = 0; k0 < cnt; k0 += B) {
-            int j[B];
-#pragma unroll
-            for (int u = 0; u < B; ++u) j[u] = (k0 + u < cnt) ? lp[(size_t)(k0 + u) * stride] : i;
-            float4 pj[B], aj[B], vj[B];
-#pragma unroll
-            for (int u = 0; u < B; ++u) {
-                pj[u] = __ldg(S.posm + j[u]);
-                aj[u] = __ldg(S.aux + j[u]);
-                vj[u] = __ldg(S.veld + j[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < B; ++u) {
-                float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
-                float r2 = rx * rx + ry * ry + rz * rz;
-                force_pair_pre(P, S, A, j[u], rx, ry, rz, r2, pj[u].w, aj[u], vj[u], vi, dpi, dpi_solid, coh_i);
-            }
-        }
-    } else {
-        for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
-                          [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
-                              force_pair(P, S, A, j, rx, ry, rz, r2, pj.w, vi, dpi, dpi_solid, coh_i);
-                          });
-    }
-    S.acc[i] = make_float4(A.npx + A.prx, A.npy + A.pry, A.npz + A.prz, 0.f);
-}
-
-template <int B, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_density_list_b(DevParams P, DevArrays S) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
-    if (P.slab_on && S.grid_ids[i] >= P.C) return;
-    float4 pi = S.posm[i];
-    float4 mi = S.misc[i];
-    uint32_t fl = __float_as_uint(mi.z);
-    if (!(fl & FLAG_FLUID)) {
-        bool dyn = (fl & FLAG_DYNAMIC) != 0;
-        S.aux[i] = make_float4(S.veld[i].w, 0.0f, dyn ? -2.0f : -1.0f, 0.0f);
-        S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
-        S.nbr_cnt[i] = 0;
-        return;
-    }
-    int cnt = 0;
-    {
-        int32_t *lp = S.nbr_list + i;
-        const size_t stride = (size_t)S.npad;
-        int ci, cj, ck;
-        cell_of(P, pi.x, pi.y, pi.z, ci, cj, ck);
-        ci = min(max(ci, 0), P.gx - 1); cj = min(max(cj, 0), P.gy - 1); ck = min(max(ck, 0), P.gz - 1);
-        int k_lo = max(ck - 1, 0), k_hi = min(ck + 1, P.gz - 1);
-        for (int dx = -1; dx <= 1; ++dx) {
-            int ni = ci + dx;
-            if (ni < 0 || ni >= P.gx) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                int nj = cj + dy;
-                if (nj < 0 || nj >= P.gy) continue;
-                int row = (ni * P.gy + nj) * P.gz;
-                int j0 = __ldg(S.cell_end + max(row + k_lo - 1, 0));
-                int j1 = __ldg(S.cell_end + row + k_hi);
-                for (int jb = j0; jb < j1; jb += B) {
-                    float4 pj[B];
-#pragma unroll
-                    for (int u = 0; u < B; ++u) pj[u] = __ldg(S.posm + min(jb + u, j1 - 1));
-#pragma unroll
-                    for (int u = 0; u < B; ++u) {
-                        int j = jb + u;
-                        float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
-                        float r2 = rx * rx + ry * ry + rz * rz;
-                        bool hit = (r2 < P.h2) && (j != i) && (j < j1);
-                        if (hit) {
-                            if (cnt < NBR_CAP) { *lp = j; lp += stride; }
-                            ++cnt;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    float den = 0.0f;
-    if (cnt <= NBR_CAP) {
-        S.nbr_cnt[i] = cnt;
-        const int32_t *lp = S.nbr_list + i;
-        const size_t stride = (size_t)S.npad;
-        for (int k0 = 0; k0 < cnt; k0 += B) {
-            float4 pj[B];
-#pragma unroll
-            for (int u = 0; u < B; ++u) {
-                int j = (k0 + u < cnt) ? lp[(size_t)(k0 + u) * stride] : i;
-                pj[u] = __ldg(S.posm + j);
-            }
-#pragma unroll
-            for (int u = 0; u < B; ++u) {
-                float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
-                float r2 = rx * rx + ry * ry + rz * rz;
-                float r, inv_r;
-                fast_norm(r2, r, inv_r);
-                float w = pj[u].w * w_cubic(P, r);
-                den += (k0 + u < cnt) ? w : 0.0f;
-            }
-        }
-    } else {
-        S.nbr_cnt[i] = NBR_OVERFLOW;
-        for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
-                          [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
-                              den += pj.w * w_cubic(P, sqrtf(r2));
-                          });
-    }
-    float rho = pi.w * P.w0;
-    rho += den;
-    rho *= P.rho0;
-    float vol = mi.x / rho;
-    float rc = fmaxf(rho, P.rho0);
-    float p = tait_pressure(P, rc);
-    reinterpret_cast<float *>(S.veld + i)[3] = rc;
-    reinterpret_cast<float *>(S.misc + i)[1] = p;
-    S.aux[i] = make_float4(vol, p / (rc * rc), mi.x, 0.0f);
-}
-
-// =====================================================================================
-// density pass v3: TMA-staged candidate windows.
-//
-// ncu on v2 (profiles/r01_v2_pair_kernels_ncu.txt): the candidate scan is co-limited by L1/TEX
-// (76 % of peak) -- the 32 particles of a warp sit in ~4-5 cells, so every per-lane LDG.128 of a
-// candidate touches 4-5 different 128-byte lines (one L1 tag cycle each).  Here each WARP stages,
-// per (dx, dy) column, the union of its lanes' candidate ranges -- one contiguous run of the
-// sorted posm array, ~0.75-1.5 KB -- into shared memory with ONE bulk async copy
-// (cp.async.bulk global -> shared, completion on an mbarrier; SASS: UBLKCP), double-buffered
-// across the 9 columns, and the lanes then scan their own sub-range with LDS.128.
-// Windows longer than WIN_CAP (sparse splashes) fall back to the direct global scan.
-// =====================================================================================
-constexpr int WIN_CAP = 128;      // particles per staged window (2 KB)
+// ---- TMA / mbarrier primitives (sm_90+ PTX, sm_100a SASS: UBLKCP.S.G, SYNCS.ARRIVE.TRANS64) ----
+constexpr int WIN_CAP = 128;   // particles per staged window (2 KB); longer windows scan global memory
 constexpr int DENS_WARPS = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -972,7 +670,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// 1-D bulk copy global -> shared::cta, bytes multiple of 16, both addresses 16-byte aligned
+// 1-D bulk copy global -> shared::cta; bytes multiple of 16, both addresses 16-byte aligned
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),
@@ -980,142 +678,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  : "memory");
 }
 
-__global__ void __launch_bounds__(DENS_WARPS * 32) k_density_tma(DevParams P, DevArrays S) {
-    __shared__ __align__(128) float4 s_win[DENS_WARPS][2][WIN_CAP];
-    __shared__ __align__(8) uint64_t s_bar[DENS_WARPS][2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane == 0) { mbar_init(&s_bar[warp][0], 1); mbar_init(&s_bar[warp][1], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncwarp();
-
-    bool live = i < P.n && !(P.slab_on && S.grid_ids[min(i, P.n - 1)] >= P.C);
-    float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), mi = pi;
-    uint32_t fl = 0;
-    if (live) { pi = S.posm[i]; mi = S.misc[i]; fl = __float_as_uint(mi.z); }
-    const bool fluid = live && (fl & FLAG_FLUID);
-    if (live && !fluid) {
-        bool dyn = (fl & FLAG_DYNAMIC) != 0;
-        S.aux[i] = make_float4(S.veld[i].w, 0.0f, dyn ? -2.0f : -1.0f, 0.0f);
-        S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
-        S.nbr_cnt[i] = 0;
-    }
-    if (__ballot_sync(0xffffffffu, fluid) == 0u) return;  // warp-uniform
-
-    int ci = 0, cj = 0, ck = 0;
-    cell_of(P, pi.x, pi.y, pi.z, ci, cj, ck);
-    ci = min(max(ci, 0), P.gx - 1); cj = min(max(cj, 0), P.gy - 1); ck = min(max(ck, 0), P.gz - 1);
-    const int k_lo = max(ck - 1, 0), k_hi = min(ck + 1, P.gz - 1);
-
-    // per-lane candidate range of column c = (dx + 1) * 3 + (dy + 1), reference visiting order
-    auto col_range = [&](int c, int &j0, int &j1) {
-        int ni = ci + c / 3 - 1, nj = cj + c % 3 - 1;
-        j0 = 0; j1 = 0;
-        if (fluid && ni >= 0 && ni < P.gx && nj >= 0 && nj < P.gy) {
-            int row = (ni * P.gy + nj) * P.gz;
-            j0 = __ldg(S.cell_end + max(row + k_lo - 1, 0));
-            j1 = __ldg(S.cell_end + row + k_hi);
-        }
-    };
-    // warp-uniform window [J0, J1) of column c and its staging into buffer b; returns the mode:
-    // 0 = empty, 1 = staged (wait on the barrier), 2 = too long, scan global memory directly
-    uint32_t phase = 0u;  // bit b = parity of the next completion of barrier b
-    auto stage = [&](int j0, int j1, int b, int &J0, int &J1) -> int {
-        bool ne = j1 > j0;
-        J0 = __reduce_min_sync(0xffffffffu, ne ? j0 : 0x7fffffff);
-        J1 = __reduce_max_sync(0xffffffffu, ne ? j1 : 0);
-        if (J1 <= J0) return 0;
-        if (J1 - J0 > WIN_CAP) return 2;
-        if (lane == 0) {
-            uint32_t bytes = (uint32_t)(J1 - J0) * 16u;
-            mbar_expect_tx(&s_bar[warp][b], bytes);
-            tma_bulk_g2s(&s_win[warp][b][0], S.posm + J0, bytes, &s_bar[warp][b]);
-        }
-        return 1;
-    };
-
-    int cnt = 0;
-    int32_t *lp = S.nbr_list + (fluid ? i : 0);
-    const size_t stride = (size_t)S.npad;
-    auto test = [&](int j, const float4 &pj) {
-        float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-        float r2 = rx * rx + ry * ry + rz * rz;
-        if (r2 < P.h2 && j != i) {
-            if (cnt < NBR_CAP) { *lp = j; lp += stride; }
-            ++cnt;
-        }
-    };
-
-    int j0n, j1n, J0n, J1n;
-    col_range(0, j0n, j1n);
-    int mode_n = stage(j0n, j1n, 0, J0n, J1n);
-    for (int c = 0; c < 9; ++c) {
-        const int b = c & 1;
-        const int j0 = j0n, j1 = j1n, J0 = J0n, mode = mode_n;
-        if (c + 1 < 9) {
-            col_range(c + 1, j0n, j1n);
-            __syncwarp();  // every lane is done reading buffer b^1 (column c - 1)
-            mode_n = stage(j0n, j1n, b ^ 1, J0n, J1n);
-        }
-        if (mode == 1) {
-            mbar_wait(&s_bar[warp][b], (phase >> b) & 1u);
-            phase ^= 1u << b;
-            const float4 *w = &s_win[warp][b][0] - J0;
-#pragma unroll 4
-            for (int j = j0; j < j1; ++j) test(j, w[j]);
-        } else if (mode == 2) {
-#pragma unroll 4
-            for (int j = j0; j < j1; ++j) test(j, __ldg(S.posm + j));
-        }
-    }
-    if (!fluid) return;
-
-    float den = 0.0f;
-    if (cnt <= NBR_CAP) {
-        S.nbr_cnt[i] = cnt;
-        const int32_t *lq = S.nbr_list + i;
-        for (int k0 = 0; k0 < cnt; k0 += 4) {
-            float4 pj[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                int j = (k0 + u < cnt) ? lq[(size_t)(k0 + u) * stride] : i;
-                pj[u] = __ldg(S.posm + j);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
-                float r2 = rx * rx + ry * ry + rz * rz;
-                float r, inv_r;
-                fast_norm(r2, r, inv_r);
-                float wv = pj[u].w * w_cubic(P, r);
-                den += (k0 + u < cnt) ? wv : 0.0f;
-            }
-        }
-    } else {
-        S.nbr_cnt[i] = NBR_OVERFLOW;
-        for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
-                          [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
-                              den += pj.w * w_cubic(P, sqrtf(r2));
-                          });
-    }
-    float rho = pi.w * P.w0;
-    rho += den;
-    rho *= P.rho0;
-    float vol = mi.x / rho;
-    float rc = fmaxf(rho, P.rho0);
-    float p = tait_pressure(P, rc);
-    reinterpret_cast<float *>(S.veld + i)[3] = rc;
-    reinterpret_cast<float *>(S.misc + i)[1] = p;
-    S.aux[i] = make_float4(vol, p / (rc * rc), mi.x, 0.0f);
-}
-
-// =====================================================================================
-// density pass v4: v3 + branch-free candidate scan.  The SASS of v3 spends ~10 of ~21
-// instructions per candidate in the divergent "append to list" branch (BSSY/BRA/STG/LEA/BSYNC,
-// taken by nearly every warp iteration because some lane almost always hits).  v4 scans 32
-// candidates at a time into a per-lane hit bitmask (one predicated LOP3 per candidate, no
-// branch, no store) and then flushes the set bits to the list in a short loop.
-// =====================================================================================
+// branch-free distance test of up to 32 candidates starting at jb -> hit bitmask
 template <bool FROM_SMEM>
 __device__ __forceinline__ uint32_t scan_chunk(const DevParams &P, const float4 *__restrict__ src, int jb, int len,
                                                int j_last, float xi, float yi, float zi) {
@@ -1135,7 +698,12 @@ __device__ __forceinline__ uint32_t scan_chunk(const DevParams &P, const float4 
     return (len >= 32) ? m : (m & ((1u << len) - 1u));
 }
 
-__global__ void __launch_bounds__(DENS_WARPS * 32) k_density_tma2(DevParams P, DevArrays S) {
+// Densities (WCSPH.py:33-43) + clamp and Tait EOS (WCSPH.py:73-76) + neighbour-list build +
+// initial accelerations of non-fluid particles (WCSPH.py:130-137).
+// INLINE_W: the density contribution of a hit is taken from the staged window while flushing the
+// bitmask; otherwise a second dense loop re-gathers the neighbours from global memory.
+template <bool INLINE_W>
+__global__ void __launch_bounds__(DENS_WARPS * 32) k_density_tma(DevParams P, DevArrays S) {
     __shared__ __align__(128) float4 s_win[DENS_WARPS][2][WIN_CAP + 32];
     __shared__ __align__(8) uint64_t s_bar[DENS_WARPS][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1160,12 +728,13 @@ __global__ void __launch_bounds__(DENS_WARPS * 32) k_density_tma2(DevParams P, D
             S.fvel[i] = make_float4(vb.x, vb.y, vb.z, dyn ? -vb.w : -__int_as_float(0x7f800000));
         }
     }
-    if (__ballot_sync(0xffffffffu, fluid) == 0u) return;
+    if (__ballot_sync(0xffffffffu, fluid) == 0u) return;  // warp-uniform
 
     int ci = 0, cj = 0, ck = 0;
     cell_of(P, pi.x, pi.y, pi.z, ci, cj, ck);
     ci = min(max(ci, 0), P.gx - 1); cj = min(max(cj, 0), P.gy - 1); ck = min(max(ck, 0), P.gz - 1);
     const int k_lo = max(ck - 1, 0), k_hi = min(ck + 1, P.gz - 1);
+    // per-lane candidate range of column c = (dx + 1) * 3 + (dy + 1), reference visiting order
     auto col_range = [&](int c, int &j0, int &j1) {
         int ni = ci + c / 3 - 1, nj = cj + c % 3 - 1;
         j0 = 0; j1 = 0;
@@ -1175,7 +744,9 @@ __global__ void __launch_bounds__(DENS_WARPS * 32) k_density_tma2(DevParams P, D
             j1 = __ldg(S.cell_end + row + k_hi);
         }
     };
-    uint32_t phase = 0u;
+    // warp-uniform window [J0, J1) and its staging into buffer b.  Returns 0 = empty, 1 = staged
+    // (wait on the barrier), 2 = longer than WIN_CAP: scan global memory directly.
+    uint32_t phase = 0u;  // bit b = parity of the next completion of barrier b
     auto stage = [&](int j0, int j1, int b, int &J0, int &J1) -> int {
         bool ne = j1 > j0;
         J0 = __reduce_min_sync(0xffffffffu, ne ? j0 : 0x7fffffff);
@@ -1191,16 +762,25 @@ __global__ void __launch_bounds__(DENS_WARPS * 32) k_density_tma2(DevParams P, D
     };
 
     int cnt = 0;
-    uint32_t widx = (uint32_t)(fluid ? i : 0);                    // index of the next list slot
+    float den = 0.0f;
+    uint32_t widx = (uint32_t)(fluid ? i : 0);  // index of the next list slot
     const uint32_t widx_cap = widx + (uint32_t)(NBR_CAP - 1) * (uint32_t)S.npad;  // last row
-    auto flush = [&](uint32_t m, int jb) {
+    auto flush = [&](uint32_t m, int jb, const float4 *src, bool smem) {
         if ((uint32_t)(i - jb) < 32u) m &= ~(1u << (i - jb));  // p_i != p_j
         while (m) {
             int b = __ffs(m) - 1;
             m &= m - 1u;
-            S.nbr_list[widx] = jb + b;           // beyond NBR_CAP the last row is overwritten (flagged below)
+            S.nbr_list[widx] = jb + b;  // beyond NBR_CAP the last row is overwritten (flagged below)
             widx = min(widx + (uint32_t)S.npad, widx_cap);
             ++cnt;
+            if (INLINE_W) {
+                float4 pj = smem ? src[jb + b] : __ldg(src + jb + b);
+                float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+                float r2 = rx * rx + ry * ry + rz * rz;
+                float r, inv_r;
+                fast_norm(r2, r, inv_r);
+                den += pj.w * w_cubic(P, r);
+            }
         }
     };
 
@@ -1212,7 +792,7 @@ __global__ void __launch_bounds__(DENS_WARPS * 32) k_density_tma2(DevParams P, D
         const int j0 = j0n, j1 = j1n, J0 = J0n, mode = mode_n;
         if (c + 1 < 9) {
             col_range(c + 1, j0n, j1n);
-            __syncwarp();
+            __syncwarp();  // every lane is done reading buffer b^1 (column c - 1)
             mode_n = stage(j0n, j1n, b ^ 1, J0n, J1n);
         }
         if (mode == 1) {
@@ -1220,65 +800,146 @@ __global__ void __launch_bounds__(DENS_WARPS * 32) k_density_tma2(DevParams P, D
             phase ^= 1u << b;
             const float4 *w = &s_win[warp][b][0] - J0;
             for (int jb = j0; jb < j1; jb += 32)
-                flush(scan_chunk<true>(P, w, jb, min(32, j1 - jb), 0, pi.x, pi.y, pi.z), jb);
+                flush(scan_chunk<true>(P, w, jb, min(32, j1 - jb), 0, pi.x, pi.y, pi.z), jb, w, true);
         } else if (mode == 2) {
             for (int jb = j0; jb < j1; jb += 32)
-                flush(scan_chunk<false>(P, S.posm, jb, min(32, j1 - jb), j1 - 1, pi.x, pi.y, pi.z), jb);
+                flush(scan_chunk<false>(P, S.posm, jb, min(32, j1 - jb), j1 - 1, pi.x, pi.y, pi.z), jb, S.posm, false);
         }
     }
     if (!fluid) return;
 
-    float den = 0.0f;
-    const size_t stride = (size_t)S.npad;
     if (cnt <= NBR_CAP) {
         S.nbr_cnt[i] = cnt;
-        const int32_t *lq = S.nbr_list + i;
-        for (int k0 = 0; k0 < cnt; k0 += 4) {
-            float4 pj[4];
+        if (!INLINE_W) {
+            const size_t stride = (size_t)S.npad;
+            const int32_t *lq = S.nbr_list + i;
+            for (int k0 = 0; k0 < cnt; k0 += 4) {
+                float4 pj[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                int j = (k0 + u < cnt) ? lq[(size_t)(k0 + u) * stride] : i;
-                pj[u] = __ldg(S.posm + j);
-            }
+                for (int u = 0; u < 4; ++u) {
+                    int j = (k0 + u < cnt) ? lq[(size_t)(k0 + u) * stride] : i;
+                    pj[u] = __ldg(S.posm + j);
+                }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
-                float r2 = rx * rx + ry * ry + rz * rz;
-                float r, inv_r;
-                fast_norm(r2, r, inv_r);
-                float wv = pj[u].w * w_cubic(P, r);
-                den += (k0 + u < cnt) ? wv : 0.0f;
+                for (int u = 0; u < 4; ++u) {
+                    float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
+                    float r2 = rx * rx + ry * ry + rz * rz;
+                    float r, inv_r;
+                    fast_norm(r2, r, inv_r);
+                    float wv = pj[u].w * w_cubic(P, r);
+                    den += (k0 + u < cnt) ? wv : 0.0f;
+                }
             }
         }
     } else {
         S.nbr_cnt[i] = NBR_OVERFLOW;
-        for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
-                          [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
-                              den += pj.w * w_cubic(P, sqrtf(r2));
-                          });
+        if (!INLINE_W) {
+            for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
+                              [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
+                                  den += pj.w * w_cubic(P, sqrtf(r2));
+                              });
+        }
     }
     float rho = pi.w * P.w0;
     rho += den;
     rho *= P.rho0;
-    float vol = mi.x / rho;
+    float vol = mi.x / rho;  // m_j / rho_j with the UNCLAMPED density (viscosity)
     float rc = fmaxf(rho, P.rho0);
     float p = tait_pressure(P, rc);
+    float dp = p / (rc * rc);
     reinterpret_cast<float *>(S.veld + i)[3] = rc;
     reinterpret_cast<float *>(S.misc + i)[1] = p;
-    S.aux[i] = make_float4(vol, p / (rc * rc), mi.x, 0.0f);
+    S.aux[i] = make_float4(vol, dp, mi.x, 0.0f);
     if (P.uniform_fluid) {
         float4 vb = S.veld[i];
         S.fpos[i] = make_float4(pi.x, pi.y, pi.z, vol);
-        S.fvel[i] = make_float4(vb.x, vb.y, vb.z, p / (rc * rc));
+        S.fvel[i] = make_float4(vb.x, vb.y, vb.z, dp);
     }
 }
 
-// =====================================================================================
-// force pass v3 (uniform fluids): 2 x 16 B gathered per neighbour instead of 3 x 16 B.
-// ncu on v2b: the force pass runs at 74 % of L1/TEX peak -- it is bound by the scattered 16-byte
-// gathers, so bytes per pair are what matters.
-// =====================================================================================
+// Fused force pass, general particle masses: 3 x 16 B gathered per neighbour.
 template <int B, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_force_general(DevParams P, DevArrays S) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    if (P.slab_on && S.grid_ids[i] >= P.C) return;
+    float4 mi = S.misc[i];
+    uint32_t fl = __float_as_uint(mi.z);
+    if (!(fl & FLAG_FLUID)) return;  // initialised by k_density_tma
+    if (fl & FLAG_GHOST) return;     // ghosts are neighbours only
+    float4 pi = S.posm[i];
+    float4 vi = S.veld[i];
+    float4 ai = S.aux[i];
+    const float dpi = ai.y;                              // p_i / rho_i^2
+    const float dpi_solid = dpi + mi.y * P.inv_rho0sq;   // + p_i / rho0^2 (Akinci mirror, WCSPH.py:59)
+    const float coh_i = P.sigma / mi.x;
+    ForceAcc A = {P.gx_, P.gy_, P.gz_, 0.f, 0.f, 0.f};
+    const int cnt = S.nbr_cnt[i];
+    if (cnt != NBR_OVERFLOW) {
+        const int32_t *lp = S.nbr_list + i;
+        const size_t stride = (size_t)S.npad;
+        for (int k0 = 0; k0 < cnt; k0 += B) {
+            int j[B];  // the tail is padded with i itself: its pair terms are exactly zero
+#pragma unroll
+            for (int u = 0; u < B; ++u) j[u] = (k0 + u < cnt) ? lp[(size_t)(k0 + u) * stride] : i;
+            float4 pj[B], aj[B], vj[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                pj[u] = __ldg(S.posm + j[u]);
+                aj[u] = __ldg(S.aux + j[u]);
+                vj[u] = __ldg(S.veld + j[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
+                float r2 = rx * rx + ry * ry + rz * rz;
+                force_pair_pre(P, S, A, j[u], rx, ry, rz, r2, pj[u].w, aj[u], vj[u], vi, dpi, dpi_solid, coh_i);
+            }
+        }
+    } else {
+        for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
+                          [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
+                              force_pair_pre(P, S, A, j, rx, ry, rz, r2, pj.w, __ldg(S.aux + j), __ldg(S.veld + j), vi,
+                                             dpi, dpi_solid, coh_i);
+                          });
+    }
+    S.acc[i] = make_float4(A.npx + A.prx, A.npy + A.pry, A.npz + A.prz, 0.f);
+}
+
+// one accepted pair, uniform-fluid packing (see DevArrays::fpos / fvel)
+__device__ __forceinline__ void force_pair_packed(const DevParams &P, const DevArrays &S, ForceAcc &A, int j, float rx,
+                                                  float ry, float rz, float r2, const float4 &pj, const float4 &vj,
+                                                  const float4 &vi, float dpi, float dpi_solid, float coh) {
+    float r, inv_r;
+    fast_norm(r2, r, inv_r);
+    float gs = gradw_scale_fast(P, r, inv_r);
+    if (vj.w >= 0.0f) {  // fluid neighbour: pj.w = m_j / rho_j, vj.w = p_j / rho_j^2
+        float w = (r2 > P.d2) ? w_cubic(P, r) : P.w_diam;
+        A.npx -= coh * rx * w; A.npy -= coh * ry * w; A.npz -= coh * rz * w;
+        float vxy = (vi.x - vj.x) * rx + (vi.y - vj.y) * ry + (vi.z - vj.z) * rz;
+        float sv = __fdividef(P.d_visc * pj.w * vxy, r * r + P.visc_eps) * gs;
+        A.npx += sv * rx; A.npy += sv * ry; A.npz += sv * rz;
+        float cp = -P.rho0 * P.fluid_mV * (dpi + vj.w) * gs;
+        A.prx += cp * rx; A.pry += cp * ry; A.prz += cp * rz;
+    } else {  // solid neighbour (Akinci 2012): pj.w = m_V_j, vj.w = -body density | -inf
+        float cp = -P.rho0 * pj.w * dpi_solid * gs;
+        float fx = cp * rx, fy = cp * ry, fz = cp * rz;
+        A.prx += fx; A.pry += fy; A.prz += fz;
+        float body_rho = -vj.w;
+        if (body_rho < 3.0e38f) {  // dynamic rigid: reaction, WCSPH.py:66-68
+            float *a = reinterpret_cast<float *>(S.acc + j);
+            atomicAdd(a + 0, -fx * P.rho0 / body_rho);
+            atomicAdd(a + 1, -fy * P.rho0 / body_rho);
+            atomicAdd(a + 2, -fz * P.rho0 / body_rho);
+        }
+    }
+}
+
+// Fused force pass for uniform fluids: 2 x 16 B gathered per neighbour from the per-step copies
+// fpos / fvel.  Because nothing reads posm / veld of OTHER particles here, FUSE_ADVECT lets the
+// epilogue integrate the particle and clamp it to the walls in place (advect + enforce_boundary_3D
+// (fluid), WCSPH.py:143-149, sph_base.py:149-179) -- one launch and one pass over the state less.
+template <int B, int THREADS, bool FUSE_ADVECT>
 __global__ void __launch_bounds__(THREADS) k_force_packed(DevParams P, DevArrays S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
@@ -1311,38 +972,39 @@ __global__ void __launch_bounds__(THREADS) k_force_packed(DevParams P, DevArrays
             for (int u = 0; u < B; ++u) {
                 float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
                 float r2 = rx * rx + ry * ry + rz * rz;
-                float r, inv_r;
-                fast_norm(r2, r, inv_r);
-                float gs = gradw_scale_fast(P, r, inv_r);
-                if (vj[u].w >= 0.0f) {  // fluid neighbour
-                    float w = (r2 > P.d2) ? w_cubic(P, r) : P.w_diam;
-                    A.npx -= coh * rx * w; A.npy -= coh * ry * w; A.npz -= coh * rz * w;
-                    float vxy = (vi.x - vj[u].x) * rx + (vi.y - vj[u].y) * ry + (vi.z - vj[u].z) * rz;
-                    float sv = __fdividef(P.d_visc * pj[u].w * vxy, r * r + P.visc_eps) * gs;
-                    A.npx += sv * rx; A.npy += sv * ry; A.npz += sv * rz;
-                    float cp = -P.rho0 * P.fluid_mV * (dpi + vj[u].w) * gs;
-                    A.prx += cp * rx; A.pry += cp * ry; A.prz += cp * rz;
-                } else {  // solid neighbour (Akinci 2012)
-                    float cp = -P.rho0 * pj[u].w * dpi_solid * gs;
-                    float fx = cp * rx, fy = cp * ry, fz = cp * rz;
-                    A.prx += fx; A.pry += fy; A.prz += fz;
-                    float body_rho = -vj[u].w;
-                    if (body_rho < 3.0e38f) {  // dynamic rigid: reaction, WCSPH.py:66-68
-                        float *a = reinterpret_cast<float *>(S.acc + j[u]);
-                        atomicAdd(a + 0, -fx * P.rho0 / body_rho);
-                        atomicAdd(a + 1, -fy * P.rho0 / body_rho);
-                        atomicAdd(a + 2, -fz * P.rho0 / body_rho);
-                    }
-                }
+                force_pair_packed(P, S, A, j[u], rx, ry, rz, r2, pj[u], vj[u], vi, dpi, dpi_solid, coh);
             }
         }
     } else {
-        float4 pim = S.posm[i], vim = S.veld[i], ai = S.aux[i];
-        const float coh_i = P.sigma / mi.x;
-        for_all_neighbors(P, S.posm, S.cell_end, i, pim.x, pim.y, pim.z,
+        // full scan over the frozen copy fpos (posm may already hold advected neighbours)
+        for_all_neighbors(P, S.fpos, S.cell_end, i, pi.x, pi.y, pi.z,
                           [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
-                              force_pair(P, S, A, j, rx, ry, rz, r2, pj.w, vim, ai.y, dpi_solid, coh_i);
+                              force_pair_packed(P, S, A, j, rx, ry, rz, r2, pj, __ldg(S.fvel + j), vi, dpi, dpi_solid, coh);
                           });
     }
-    S.acc[i] = make_float4(A.npx + A.prx, A.npy + A.pry, A.npz + A.prz, 0.f);
+    float4 a = make_float4(A.npx + A.prx, A.npy + A.pry, A.npz + A.prz, 0.f);
+    S.acc[i] = a;
+    if (FUSE_ADVECT && (fl & FLAG_DYNAMIC)) {
+        float4 p = make_float4(pi.x, pi.y, pi.z, P.fluid_mV);
+        float4 v = make_float4(vi.x, vi.y, vi.z, S.veld[i].w);
+        v.x += P.dt * a.x; v.y += P.dt * a.y; v.z += P.dt * a.z;
+        p.x += P.dt * v.x; p.y += P.dt * v.y; p.z += P.dt * v.z;
+        wall_clamp(P, p, v);
+        S.posm[i] = p;
+        S.veld[i] = v;
+    }
+}
+
+// advect (WCSPH.py:143-149) for the dynamic SOLID particles only (companion of FUSE_ADVECT)
+__global__ void k_advect_solids(DevParams P, DevArrays S) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.n_solid) return;
+    int i = S.solid_slot[s];
+    uint32_t fl = __float_as_uint(S.misc[i].z);
+    if (!(fl & FLAG_DYNAMIC)) return;
+    float4 p = S.posm[i], v = S.veld[i], a = S.acc[i];
+    v.x += P.dt * a.x; v.y += P.dt * a.y; v.z += P.dt * a.z;
+    p.x += P.dt * v.x; p.y += P.dt * v.y; p.z += P.dt * v.z;
+    S.posm[i] = p;
+    S.veld[i] = v;
 }
