@@ -11,7 +11,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libsph_b200.so")
+LIB_PATH = os.environ.get("SPH_B200_LIB") or os.path.join(_PKG, "libsph_b200.so")  # override: experiments only
 CSRC = os.path.join(_PKG, "csrc")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",

@@ -649,7 +649,10 @@ __device__ __forceinline__ void force_pair_pre(const DevParams &P, const DevArra
 }
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX, sm_100a SASS: UBLKCP.S.G, SYNCS.ARRIVE.TRANS64) ----
-constexpr int WIN_CAP = 128;   // particles per staged window (2 KB); longer windows scan global memory
+#ifndef WIN_CAP_VALUE
+#define WIN_CAP_VALUE 128
+#endif
+constexpr int WIN_CAP = WIN_CAP_VALUE;   // particles per staged window (2 KB); longer windows scan global memory
 constexpr int DENS_WARPS = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -678,11 +681,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  : "memory");
 }
 
-// branch-free distance test of up to 32 candidates starting at jb -> hit bitmask
+// Branch-free distance test of up to 32 candidates starting at jb.  d = |r|^2 - h^2 comes straight
+// out of a 3-FFMA chain and its sign bit is funnel-shifted into the mask (one SHF per candidate),
+// so the FIRST candidate ends up in the HIGHEST of the `len` valid bits: candidate u <-> bit len-1-u.
 template <bool FROM_SMEM>
 __device__ __forceinline__ uint32_t scan_chunk(const DevParams &P, const float4 *__restrict__ src, int jb, int len,
                                                int j_last, float xi, float yi, float zi) {
     uint32_t m = 0u;
+    int done = 0;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         if (g * 8 < len) {
@@ -690,20 +696,24 @@ __device__ __forceinline__ uint32_t scan_chunk(const DevParams &P, const float4 
             for (int u = g * 8; u < g * 8 + 8; ++u) {
                 float4 pj = FROM_SMEM ? src[jb + u] : __ldg(src + min(jb + u, j_last));
                 float rx = xi - pj.x, ry = yi - pj.y, rz = zi - pj.z;
-                float r2 = rx * rx + ry * ry + rz * rz;
-                m |= (r2 < P.h2) ? (1u << u) : 0u;
+                float d = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, -P.h2)));
+                m = __funnelshift_l(__float_as_uint(d), m, 1);
             }
+            done = g * 8 + 8;
         }
     }
-    return (len >= 32) ? m : (m & ((1u << len) - 1u));
+    return m >> (done - len);  // drop the padding candidates of the last group
 }
 
 // Densities (WCSPH.py:33-43) + clamp and Tait EOS (WCSPH.py:73-76) + neighbour-list build +
 // initial accelerations of non-fluid particles (WCSPH.py:130-137).
 // INLINE_W: the density contribution of a hit is taken from the staged window while flushing the
 // bitmask; otherwise a second dense loop re-gathers the neighbours from global memory.
+#ifndef DENS_MIN_BLOCKS
+#define DENS_MIN_BLOCKS 9  // 56 registers: measured best (profiles/)
+#endif
 template <bool INLINE_W>
-__global__ void __launch_bounds__(DENS_WARPS * 32) k_density_tma(DevParams P, DevArrays S) {
+__global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tma(DevParams P, DevArrays S) {
     __shared__ __align__(128) float4 s_win[DENS_WARPS][2][WIN_CAP + 32];
     __shared__ __align__(8) uint64_t s_bar[DENS_WARPS][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -765,11 +775,12 @@ __global__ void __launch_bounds__(DENS_WARPS * 32) k_density_tma(DevParams P, De
     float den = 0.0f;
     uint32_t widx = (uint32_t)(fluid ? i : 0);  // index of the next list slot
     const uint32_t widx_cap = widx + (uint32_t)(NBR_CAP - 1) * (uint32_t)S.npad;  // last row
-    auto flush = [&](uint32_t m, int jb, const float4 *src, bool smem) {
-        if ((uint32_t)(i - jb) < 32u) m &= ~(1u << (i - jb));  // p_i != p_j
+    auto flush = [&](uint32_t m, int jb, int len, const float4 *src, bool smem) {
+        if ((uint32_t)(i - jb) < (uint32_t)len) m &= ~(1u << (len - 1 - (i - jb)));  // p_i != p_j
         while (m) {
-            int b = __ffs(m) - 1;
-            m &= m - 1u;
+            int hb = 31 - __clz(m);  // highest set bit = earliest candidate: keeps the reference order
+            m &= ~(1u << hb);
+            int b = len - 1 - hb;
             S.nbr_list[widx] = jb + b;  // beyond NBR_CAP the last row is overwritten (flagged below)
             widx = min(widx + (uint32_t)S.npad, widx_cap);
             ++cnt;
@@ -799,11 +810,15 @@ __global__ void __launch_bounds__(DENS_WARPS * 32) k_density_tma(DevParams P, De
             mbar_wait(&s_bar[warp][b], (phase >> b) & 1u);
             phase ^= 1u << b;
             const float4 *w = &s_win[warp][b][0] - J0;
-            for (int jb = j0; jb < j1; jb += 32)
-                flush(scan_chunk<true>(P, w, jb, min(32, j1 - jb), 0, pi.x, pi.y, pi.z), jb, w, true);
+            for (int jb = j0; jb < j1; jb += 32) {
+                const int len = min(32, j1 - jb);
+                flush(scan_chunk<true>(P, w, jb, len, 0, pi.x, pi.y, pi.z), jb, len, w, true);
+            }
         } else if (mode == 2) {
-            for (int jb = j0; jb < j1; jb += 32)
-                flush(scan_chunk<false>(P, S.posm, jb, min(32, j1 - jb), j1 - 1, pi.x, pi.y, pi.z), jb, S.posm, false);
+            for (int jb = j0; jb < j1; jb += 32) {
+                const int len = min(32, j1 - jb);
+                flush(scan_chunk<false>(P, S.posm, jb, len, j1 - 1, pi.x, pi.y, pi.z), jb, len, S.posm, false);
+            }
         }
     }
     if (!fluid) return;
