@@ -245,6 +245,14 @@ def run_single(args):
     ps.download_state(hx, hv)
     torch.cuda.synchronize()
     Ke = max(3, min(K, 100))
+    # link diagnostic: the same pinned buffers, copies only (explains e2e on boxes with a slow PCIe path)
+    dx = torch.empty_like(hx, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        dx.copy_(hx, non_blocking=True); hv.copy_(dx, non_blocking=True)
+    torch.cuda.synchronize()
+    link_gbs = 5 * 2 * hx.numel() * 4 / (time.perf_counter() - t0) / 1e9
     for _ in range(3):
         ps.upload_state(hx, hv); solver.step(); ps.download_state(hx, hv)
     torch.cuda.synchronize()
@@ -276,6 +284,7 @@ def run_single(args):
         "e2e": {"value": Ke / e2e_s * n / 1e6, "unit": UNIT, "steps_per_s": Ke / e2e_s, "steps": Ke,
                 "h2d_bytes_per_step": int(n * 24),
                 "d2h_bytes_per_step": int(n * 24),
+                "pinned_copy_gbs_this_box": round(link_gbs, 2),
                 "note": "ParticleSystem.upload_state -> WCSPHSolver.step -> download_state, pinned host x and v"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_force<NP,PR> (fused non-pressure + pressure pass)", "bound": "hbm",
