@@ -26,8 +26,8 @@ inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
     uint64_t off_state[13];  // posm, veld, x0id, misc, acc (x2), aux, fpos, fvel
-    uint64_t off_cid, off_grid_ids, off_perm;
-    uint64_t off_zero_begin, off_tile_counter, off_tile_state, off_cell_end, off_cell_fill, off_zero_end;
+    uint64_t off_cid, off_grid_ids, off_perm, off_ticket;
+    uint64_t off_zero_begin, off_tile_counter, off_tile_state, off_cell_end, off_zero_end;
     uint64_t off_solid_slot, off_status, off_bodies, off_scratch, off_nbr_list, off_nbr_cnt;
     int64_t npad;
     uint64_t total;
@@ -43,13 +43,13 @@ Layout make_layout(int64_t n_max, int64_t C, int64_t n_solid, int n_bodies) {
     L.off_cid = take(n * 4);
     L.off_grid_ids = take(n * 4);
     L.off_perm = take(n * 4);
+    L.off_ticket = take(n * 4);
     L.n_tiles = (int)((C + 1 + SCAN_TILE - 1) / SCAN_TILE);  // +1: the slab-mode trash bucket
     // one contiguous region that a single memset clears every build
     L.off_zero_begin = o;
     L.off_tile_counter = take(256);
     L.off_tile_state = take((uint64_t)L.n_tiles * 8);
     L.off_cell_end = take((uint64_t)(C + 1) * 4);
-    L.off_cell_fill = take((uint64_t)(C + 1) * 4);
     L.off_zero_end = o;
     L.off_solid_slot = take((uint64_t)(n_solid > 0 ? n_solid : 1) * 4);
     L.off_status = take(256);
@@ -85,6 +85,8 @@ struct SphCtx {
     int64_t graph_multi_kernels[2] = {0, 0};
     int parity = 0;
     int var_density = 1, var_force = 1;  // 1 = production; 0 = ablation variants (SPH_DENSITY_VARIANT / SPH_FORCE_VARIANT)
+    bool time_pair = false;
+    cudaEvent_t pair_ev[3] = {nullptr, nullptr, nullptr};
     cudaStream_t capture_stream = nullptr;  // graphs are captured here (the legacy stream cannot capture)
     bool built = false;  // neighbour structure valid for current positions
 };
@@ -155,7 +157,7 @@ void bind_arrays(SphCtx *c) {
     S.tile_counter = reinterpret_cast<int32_t *>(w + L.off_tile_counter);
     S.tile_state = reinterpret_cast<unsigned long long *>(w + L.off_tile_state);
     S.cell_end = reinterpret_cast<int32_t *>(w + L.off_cell_end);
-    S.cell_fill = reinterpret_cast<int32_t *>(w + L.off_cell_fill);
+    S.ticket = reinterpret_cast<int32_t *>(w + L.off_ticket);
     S.solid_slot = reinterpret_cast<int32_t *>(w + L.off_solid_slot);
     S.status = reinterpret_cast<uint32_t *>(w + L.off_status);
     S.nbr_list = reinterpret_cast<int32_t *>(w + L.off_nbr_list);
@@ -191,7 +193,7 @@ struct StageTimer {
 };
 
 // particle_system.py:372-375.  Kernel count returned through *kernels.
-int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels) {
+int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels, bool move_acc = true) {
     const DevParams &P = c->P;
     if (P.n == 0) return SPH_OK;
     const Layout &L = c->L;
@@ -204,7 +206,8 @@ int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *k
     if (tm) tm->mark(T_BUCKET);
     k_bucket<<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
     if (tm) tm->mark(T_MOVE);
-    k_rank_move<<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
+    if (move_acc) k_rank_move<true><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
+    else k_rank_move<false><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
     *kernels += 4;
     CUDA_TRY(c, cudaGetLastError());
     c->parity ^= 1;  // sorted state now lives in the other buffer set
@@ -244,7 +247,7 @@ void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, in
 int launch_boundary_volume(SphCtx *c, int moving, cudaStream_t st, int64_t *kernels) {
     const DevParams &P = c->P;
     if (P.n_solid == 0) return SPH_OK;
-    k_boundary_volume<<<blocks_for(P.n_solid, 128), 128, 0, st>>>(P, c->S, moving);
+    k_boundary_volume<<<blocks_for((int64_t)P.n_solid * 32, 128), 128, 0, st>>>(P, c->S, moving);
     *kernels += 1;
     CUDA_TRY(c, cudaGetLastError());
     return SPH_OK;
@@ -265,7 +268,7 @@ int launch_rigid_solve(SphCtx *c, cudaStream_t st, int64_t *kernels) {
 int launch_step(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels) {
     const DevParams &P = c->P;
     if (P.n == 0) return SPH_OK;
-    int rc = launch_neighbor_build(c, st, tm, kernels);
+    int rc = launch_neighbor_build(c, st, tm, kernels, /*move_acc=*/false);
     if (rc) return rc;
     if (tm) tm->mark(T_BVOL);
     if (c->has_dynamic_solids) { rc = launch_boundary_volume(c, 1, st, kernels); if (rc) return rc; }
@@ -617,7 +620,7 @@ int sph_slab_step(SphCtx *ctx, int32_t *info_dev, int32_t sort_only, void *strea
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const DevParams &P = ctx->P;
     if (P.n == 0) { CUDA_TRY(ctx, cudaMemsetAsync(info_dev, 0, 32, st)); return SPH_OK; }
-    int rc = launch_neighbor_build(ctx, st, nullptr, &ctx->launches);
+    int rc = launch_neighbor_build(ctx, st, nullptr, &ctx->launches, /*move_acc=*/false);
     if (rc) return rc;
     k_slab_info<<<1, 32, 0, st>>>(P, ctx->S, info_dev);
     ctx->launches += 1;
@@ -634,10 +637,33 @@ int sph_slab_compute(SphCtx *ctx, void *stream) {
     if (P.n == 0) return SPH_OK;
     if (!ctx->built) return fail(ctx, SPH_E_ARG, "sph_slab_compute needs a fresh sph_slab_step(sort_only = 1)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    launch_pair_density(ctx, st, &ctx->launches);
-    launch_pair_force_and_advect(ctx, st, nullptr, &ctx->launches);
+    if (ctx->time_pair) {  // CUDA events around the two pair kernels (bench.py roofline at N > 1)
+        for (int k = 0; k < 3; ++k)
+            if (!ctx->pair_ev[k]) CUDA_TRY(ctx, cudaEventCreate(&ctx->pair_ev[k]));
+        cudaEventRecord(ctx->pair_ev[0], st);
+        launch_pair_density(ctx, st, &ctx->launches);
+        cudaEventRecord(ctx->pair_ev[1], st);
+        launch_pair_force_and_advect(ctx, st, nullptr, &ctx->launches);
+        cudaEventRecord(ctx->pair_ev[2], st);
+    } else {
+        launch_pair_density(ctx, st, &ctx->launches);
+        launch_pair_force_and_advect(ctx, st, nullptr, &ctx->launches);
+    }
     ctx->built = false;
     CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
+// Enable / read the CUDA-event timing of the last sph_slab_compute: ms_out = {density, force}.
+// Reading synchronises on the recorded events.
+int sph_slab_pair_times(SphCtx *ctx, int32_t enable, float *ms_out) {
+    if (!ctx) return SPH_E_ARG;
+    if (ms_out && ctx->time_pair && ctx->pair_ev[2]) {
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->pair_ev[2]));
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms_out[0], ctx->pair_ev[0], ctx->pair_ev[1]));
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms_out[1], ctx->pair_ev[1], ctx->pair_ev[2]));
+    }
+    ctx->time_pair = enable != 0;
     return SPH_OK;
 }
 

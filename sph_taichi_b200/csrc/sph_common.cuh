@@ -54,7 +54,7 @@ struct DevArrays {
     int32_t *grid_ids;  // cell id per particle in sorted order (public grid_ids)
     int32_t *perm;      // bucket slot -> pre-sort index
     int32_t *cell_end;  // [C] inclusive prefix sum (public grid_particles_num)
-    int32_t *cell_fill; // [C] bucket fill counters
+    int32_t *ticket;    // arrival ticket of each particle inside its cell (from the histogram atomic)
     unsigned long long *tile_state;
     int32_t *tile_counter;
     int32_t *solid_slot;  // [n_solid] solid_id -> sorted index

@@ -100,9 +100,17 @@ __global__ void k_hash_count(DevParams P, DevArrays S) {
         S.cid[i] = c;
     }
     // the trash bucket collects ~10 % of all records in slab mode: one atomic per warp, not per lane
+    // The histogram atomic also hands out the arrival ticket inside the cell, which k_bucket turns
+    // into a slot after the scan -- no second round of atomics.
     const unsigned trash = __ballot_sync(0xffffffffu, active && c == P.C);
-    if (active && c != P.C) atomicAdd(S.cell_end + c, 1);
-    if (trash && (threadIdx.x & 31) == (__ffs(trash) - 1)) atomicAdd(S.cell_end + P.C, __popc(trash));
+    if (active && c != P.C) S.ticket[i] = atomicAdd(S.cell_end + c, 1);
+    if (trash) {
+        const int lane = threadIdx.x & 31, leader = __ffs(trash) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(S.cell_end + P.C, __popc(trash));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (active && c == P.C) S.ticket[i] = base + __popc(trash & ((1u << lane) - 1u));
+    }
 }
 
 // After the sort: live count and the index ranges of the boundary layers this rank must send
@@ -221,31 +229,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int32_t *__restrict__ dat
 
 __global__ void k_bucket(DevParams P, DevArrays S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < P.n;
-    const int lane = threadIdx.x & 31;
-    int c = active ? S.cid[i] : -1;
-    const unsigned trash = __ballot_sync(0xffffffffu, active && c == P.C);
-    if (active && c != P.C) {
-        int start = c > 0 ? S.cell_end[c - 1] : 0;
-        int slot = start + atomicAdd(S.cell_fill + c, 1);
-        S.perm[slot] = i;
-    }
-    if (trash) {  // warp-aggregated ticket for the trash bucket
-        const int leader = __ffs(trash) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(S.cell_fill + P.C, __popc(trash));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (active && c == P.C) {
-            int slot = S.cell_end[P.C - 1] + base + __popc(trash & ((1u << lane) - 1u));
-            S.perm[slot] = i;
-        }
-    }
+    if (i >= P.n) return;
+    int c = S.cid[i];
+    int start = c > 0 ? S.cell_end[c - 1] : 0;
+    S.perm[start + S.ticket[i]] = i;
 }
 
 // The atomic tickets above give an arbitrary order inside a cell (as in the reference on a
 // GPU).  Ranking every bucket entry by its pre-sort index makes the result the
 // STABLE counting sort -- the serial semantics of particle_system.py:325-330 -- so the sorted
 // arrays are bit-reproducible and identical to the oracle's.
+template <bool MOVE_ACC>
 __global__ void k_rank_move(DevParams P, DevArrays S) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.n) return;
@@ -264,7 +258,7 @@ __global__ void k_rank_move(DevParams P, DevArrays S) {
     S.veld_n[dst] = S.veld[src];
     S.x0id_n[dst] = S.x0id[src];
     S.misc_n[dst] = misc;
-    S.acc_n[dst] = S.acc[src];
+    if (MOVE_ACC) S.acc_n[dst] = S.acc[src];  // the fused step overwrites every acceleration anyway
     S.grid_ids[dst] = c;
     int sid = __float_as_int(misc.w);
     if (sid >= 0) S.solid_slot[sid] = dst;
@@ -275,23 +269,47 @@ __global__ void k_rank_move(DevParams P, DevArrays S) {
 // reference-named un-fused entry points and are the fallback for over-full neighbour lists.
 // =====================================================================================
 
-// Akinci boundary volumes (sph_base.py:91-113).  One thread per SOLID particle.
+// Akinci boundary volumes (sph_base.py:91-113).  One WARP per solid particle: the lanes stride
+// over the candidates of the 9 column runs and the partial sums are tree-reduced (a thread per
+// particle left most of the GPU idle: a body has only a few thousand particles).
 __global__ void __launch_bounds__(128) k_boundary_volume(DevParams P, DevArrays S, int moving) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.n_solid) return;
-    int i = S.solid_slot[s];
-    uint32_t fl = __float_as_uint(S.misc[i].z);
-    bool dyn = (fl & FLAG_DYNAMIC) != 0;
+    const int lane = threadIdx.x & 31;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= P.n_solid) return;  // warp-uniform
+    const int i = S.solid_slot[s];
+    const uint32_t fl = __float_as_uint(S.misc[i].z);
+    const bool dyn = (fl & FLAG_DYNAMIC) != 0;
     if (dyn != (moving != 0)) return;
-    float4 pi = S.posm[i];
-    float delta = P.w0;
-    for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
-                      [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
-                          uint32_t fj = __float_as_uint(__ldg(&S.misc[j].z));
-                          if (!(fj & FLAG_FLUID)) delta += w_cubic(P, sqrtf(r2));
-                      });
+    const float4 pi = S.posm[i];
+    int ci, cj, ck;
+    cell_of(P, pi.x, pi.y, pi.z, ci, cj, ck);
+    ci = min(max(ci, 0), P.gx - 1); cj = min(max(cj, 0), P.gy - 1); ck = min(max(ck, 0), P.gz - 1);
+    const int k_lo = max(ck - 1, 0), k_hi = min(ck + 1, P.gz - 1);
+    float part = 0.0f;
+    for (int dx = -1; dx <= 1; ++dx) {
+        int ni = ci + dx;
+        if (ni < 0 || ni >= P.gx) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+            int nj = cj + dy;
+            if (nj < 0 || nj >= P.gy) continue;
+            int row = (ni * P.gy + nj) * P.gz;
+            int j0 = __ldg(S.cell_end + max(row + k_lo - 1, 0));
+            int j1 = __ldg(S.cell_end + row + k_hi);
+            for (int j = j0 + lane; j < j1; j += 32) {
+                float4 pj = __ldg(S.posm + j);
+                float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+                float r2 = rx * rx + ry * ry + rz * rz;
+                if (r2 < P.h2 && j != i) {
+                    uint32_t fj = __float_as_uint(__ldg(&S.misc[j].z));
+                    if (!(fj & FLAG_FLUID)) part += w_cubic(P, sqrtf(r2));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     // only .w changes; concurrent readers use .xyz only
-    reinterpret_cast<float *>(S.posm + i)[3] = 1.0f / delta * 3.0f;
+    if (lane == 0) reinterpret_cast<float *>(S.posm + i)[3] = 1.0f / (P.w0 + part) * 3.0f;
 }
 
 // Densities (WCSPH.py:33-43).  FUSE_EOS additionally applies the clamp + Tait EOS of
@@ -504,23 +522,28 @@ __device__ __forceinline__ void block_reduce(float (&v)[NV], float *smem /* [32 
     }
 }
 
+// Rotation factor of the polar decomposition A = R S (what ti.polar_decompose returns for R):
+// scaled Newton iteration X <- (g X + X^-T / g) / 2 in fp64 on one thread; 3 divisions and 2 square
+// roots per iteration (fp64 latency is what this single thread pays for), ~8 iterations.
 __device__ void polar_rotation_f64(const double A[9], double R[9], bool &ok) {
     double X[9];
     for (int i = 0; i < 9; ++i) X[i] = A[i];
     ok = true;
     for (int it = 0; it < 100; ++it) {
-        double c[9];
+        double c[9];  // cofactors: X^-T = c / det
         c[0] = X[4] * X[8] - X[5] * X[7]; c[1] = X[5] * X[6] - X[3] * X[8]; c[2] = X[3] * X[7] - X[4] * X[6];
         c[3] = X[2] * X[7] - X[1] * X[8]; c[4] = X[0] * X[8] - X[2] * X[6]; c[5] = X[1] * X[6] - X[0] * X[7];
         c[6] = X[1] * X[5] - X[2] * X[4]; c[7] = X[2] * X[3] - X[0] * X[5]; c[8] = X[0] * X[4] - X[1] * X[3];
         double det = X[0] * c[0] + X[1] * c[1] + X[2] * c[2];
         if (fabs(det) < 1e-300) { ok = false; break; }
+        const double inv_det = 1.0 / det;
         double nx = 0, ni = 0;
-        for (int i = 0; i < 9; ++i) { nx += X[i] * X[i]; ni += (c[i] / det) * (c[i] / det); }
-        double gamma = sqrt(sqrt(ni / nx));
+        for (int i = 0; i < 9; ++i) { c[i] *= inv_det; nx += X[i] * X[i]; ni += c[i] * c[i]; }
+        const double gamma = sqrt(sqrt(ni / nx));  // Frobenius-norm scaling
+        const double inv_gamma = 1.0 / gamma;
         double diff = 0;
         for (int i = 0; i < 9; ++i) {
-            double y = 0.5 * (gamma * X[i] + (c[i] / det) / gamma);
+            double y = 0.5 * (gamma * X[i] + c[i] * inv_gamma);
             diff += (y - X[i]) * (y - X[i]);
             X[i] = y;
         }
@@ -529,24 +552,38 @@ __device__ void polar_rotation_f64(const double A[9], double R[9], bool &ok) {
     for (int i = 0; i < 9; ++i) R[i] = X[i];
 }
 
-// mode 0: compute_com -> out[3];  mode 1: store rest cm;  mode 2: solve_constraints
+// mode 0: compute_com -> out[3];  mode 1: store rest cm;  mode 2: solve_constraints.
+// One gather pass accumulates the raw moments  M = sum m,  X = sum m x,  Q = sum m q,  XQ = sum m x (x) q
+// (q = x_0 - rest_cm); then  cm = X / M  and  A = sum m (x - cm) (x) q = XQ - cm (x) Q  (sph_base.py:182-211).
 __global__ void __launch_bounds__(RIGID_THREADS) k_rigid(DevParams P, DevArrays S, RigidBodyDev *bodies, int body,
                                                           int mode, float *out) {
-    __shared__ float red[32 * 9];
+    __shared__ float red[32 * 16];
     __shared__ float s_R[9];
     RigidBodyDev *B = bodies + body;
     const int b0 = B->solid_begin, b1 = B->solid_end;
-    float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+    const float r0 = B->rest_cm[0], r1 = B->rest_cm[1], r2 = B->rest_cm[2];
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
     for (int s = b0 + threadIdx.x; s < b1; s += blockDim.x) {
         int i = S.solid_slot[s];
         uint32_t fl = __float_as_uint(S.misc[i].z);
         if (!(fl & FLAG_DYNAMIC)) continue;  // compute_com counts dynamic rigid particles only (Q8)
-        float4 p = S.posm[i];
+        float4 p = S.posm[i], x0 = S.x0id[i];
         float mass = P.m_V0 * S.veld[i].w;
-        acc4[0] += mass * p.x; acc4[1] += mass * p.y; acc4[2] += mass * p.z; acc4[3] += mass;
+        float q[3] = {x0.x - r0, x0.y - r1, x0.z - r2};
+        float x[3] = {p.x, p.y, p.z};
+        acc[0] += mass;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            acc[1 + r] += mass * x[r];
+            acc[4 + r] += mass * q[r];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[7 + 3 * r + c] += mass * x[r] * q[c];
+        }
     }
-    block_reduce<4>(acc4, red);
-    const float cmx = acc4[0] / acc4[3], cmy = acc4[1] / acc4[3], cmz = acc4[2] / acc4[3];
+    block_reduce<16>(acc, red);
+    const float cmx = acc[1] / acc[0], cmy = acc[2] / acc[0], cmz = acc[3] / acc[0];
     if (mode == 0) {
         if (threadIdx.x == 0) { out[0] = cmx; out[1] = cmy; out[2] = cmz; }
         return;
@@ -555,25 +592,11 @@ __global__ void __launch_bounds__(RIGID_THREADS) k_rigid(DevParams P, DevArrays 
         if (threadIdx.x == 0) { B->rest_cm[0] = cmx; B->rest_cm[1] = cmy; B->rest_cm[2] = cmz; }
         return;
     }
-    const float r0 = B->rest_cm[0], r1 = B->rest_cm[1], r2 = B->rest_cm[2];
-    float A[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int s = b0 + threadIdx.x; s < b1; s += blockDim.x) {
-        int i = S.solid_slot[s];
-        uint32_t fl = __float_as_uint(S.misc[i].z);
-        if (!(fl & FLAG_DYNAMIC)) continue;
-        float4 p = S.posm[i], x0 = S.x0id[i];
-        float w = P.m_V0 * S.veld[i].w;
-        float q[3] = {x0.x - r0, x0.y - r1, x0.z - r2};
-        float pp[3] = {p.x - cmx, p.y - cmy, p.z - cmz};
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) A[3 * r + c] += w * pp[r] * q[c];
-    }
-    block_reduce<9>(A, red);
     if (threadIdx.x == 0) {
+        const float cm[3] = {cmx, cmy, cmz};
         double Ad[9], Rd[9];
-        for (int k = 0; k < 9; ++k) Ad[k] = (double)A[k];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) Ad[3 * r + c] = (double)acc[7 + 3 * r + c] - (double)cm[r] * (double)acc[4 + c];
         bool ok;
         polar_rotation_f64(Ad, Rd, ok);
         if (!ok) atomicOr(S.status, SPH_STATUS_BAD_POLAR);

@@ -150,6 +150,12 @@ class EngineBackend:
     def launch_count(self):
         return self.eng.launch_count()
 
+    def pair_times(self, enable=True):
+        """Switch the per-kernel CUDA-event timing on/off; returns (density_ms, force_ms) of the last timed step."""
+        buf = (C.c_float * 2)(0.0, 0.0)
+        self.eng._check(self.eng.lib.sph_slab_pair_times(self.eng.ctx, int(enable), buf), "sph_slab_pair_times")
+        return float(buf[0]), float(buf[1])
+
     def synchronize(self):
         torch.cuda.synchronize(self.device)
 
@@ -370,6 +376,21 @@ def bench_main(args):
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler else None
 
+    # ---- force-kernel roofline on every rank (CUDA events around the launch, 10 extra steps) ----
+    sim.b.pair_times(True)
+    fsum = dsum = 0.0
+    for _ in range(10):
+        sim.step()
+        d_ms, f_ms = sim.b.pair_times(True)
+        dsum += d_ms / 10
+        fsum += f_ms / 10
+    sim.b.pair_times(False)
+    owned_now = sim.owned_count()
+    peak, peak_src = _bench.measured_hbm_peak()
+    roof = torch.tensor([fsum, dsum, float(owned_now)], device=dev, dtype=torch.float64)
+    roof_max = roof.clone()
+    dist.all_reduce(roof_max, op=dist.ReduceOp.MAX)
+
     # ---- e2e: every step, H2D of the live records' {x, m_V} and {v, rho} words from pinned host
     # memory, the sharded step, and D2H of the same words (what a host-side consumer reads) ----
     Ke = max(3, min(K, 50))
@@ -428,8 +449,15 @@ def bench_main(args):
                     "note": "per rank and step: pinned-host -> device copy of the live records' position and velocity "
                             "words, sharded step (NCCL halo exchange inside), device -> pinned-host copy back; max over ranks"},
             "gpu_launches": int(tot[2].item()),
-            "roofline": None, "cpu_baseline": None,
-            "notes": "roofline and cpu_baseline are reported by the N = 1 run (bench.py contract)",
+            "roofline": {"kernel": "force pass (k_force_packed), slowest rank", "bound": "hbm",
+                         "achieved": _bench.FORCE_BYTES_PER_PARTICLE * float(roof_max[2].item()) / (float(roof_max[0].item()) * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s",
+                         "frac": _bench.FORCE_BYTES_PER_PARTICLE * float(roof_max[2].item()) / (float(roof_max[0].item()) * 1e-3) / 1e9 / peak,
+                         "traffic": None, "peak_source": peak_src, "avg_launch_ms": float(roof_max[0].item()),
+                         "density_launch_ms": float(roof_max[1].item()), "owned_particles_slowest_rank": int(roof_max[2].item()),
+                         "note": "per GPU; algorithmic 52 B x owned particles / CUDA-event time; pair kernels are issue bound"},
+            "cpu_baseline": None,
+            "notes": "cpu_baseline is reported by the N = 1 run and by --impl reference (bench.py contract)",
         }
         print(json.dumps(line))
     dist.barrier()
