@@ -269,6 +269,8 @@ class ParticleSystem:
         """Positions / velocities of one object in the current sorted order (particle_system.py:409-418)."""
         self._push()
         n = int(self.particle_num[None])
+        if n == 0:
+            return {"position": np.zeros((0, 3), np.float32), "velocity": np.zeros((0, 3), np.float32)}
         x = torch.empty((n, 3), dtype=torch.float32, device=self.device)
         v = torch.empty((n, 3), dtype=torch.float32, device=self.device)
         oid = torch.empty(n, dtype=torch.int32, device=self.device)
