@@ -230,7 +230,7 @@ def run_single(args):
 
     # ---- per-kernel stage times (CUDA events between launches, un-graphed steps) ----
     stages = {}
-    P = 20
+    P = 20 if sc["Configuration"]["simulationMethod"] == 0 else 0  # the stage profiler covers the WCSPH step
     for _ in range(P):
         for k_, v_ in eng.profile_step().items():
             stages[k_] = stages.get(k_, 0.0) + v_ / P
@@ -277,7 +277,9 @@ def run_single(args):
                    "note": "back-to-back CUDA-graph steps, state L2-resident (no flush)"},
         "readme_rtx3090_steps_per_s": 280.0 if name == "dragon_bath" else None,
         "config": {"workload": name, "particles": n, "fluid_particles": ps.fluid_particle_num,
-                   "grid_cells": int(ps.grid_num.prod()), "solver": "WCSPH", "dt": sc["Configuration"]["timeStepSize"],
+                   "grid_cells": int(ps.grid_num.prod()),
+                   "solver": "WCSPH" if sc["Configuration"]["simulationMethod"] == 0 else "DFSPH",
+                   "dt": sc["Configuration"]["timeStepSize"],
                    "l2": "flushed between timed steps (256 MiB write); 'steady' is un-flushed",
                    "parallelism": "single GPU"},
         "clocks": clocks,

@@ -77,6 +77,7 @@ typedef struct SphFields {
     int32_t *color;    /* [n][3], each component must be in 0..255 */
     int32_t *grid_ids; /* output only (particle_system.py:138) */
     int32_t *solid_id; /* input only */
+    float *dfsph_factor, *density_adv; /* DFSPH, output only, may be NULL (particle_system.py:115-117) */
 } SphFields;
 
 /* One dynamic rigid body registered for shape matching (sph_base.py:200-260). */
@@ -141,6 +142,19 @@ int sph_solve_constraints(SphCtx *ctx, int32_t body_index, float *R_out_dev, voi
 /* ---- SPHBase.step (sph_base.py:263-271) + WCSPHSolver.substep (WCSPH.py:152-156) ---------- */
 /* nsteps whole steps with the fused kernels, replayed from a CUDA graph. */
 int sph_step(SphCtx *ctx, int32_t nsteps, void *stream);
+
+/* ---- DFSPH (reference DFSPH.py, simulationMethod 4) ---------------------
+ * One entry point, `op` selects the reference kernel (names as in DFSPH.py):
+ *   0 compute_densities (:39-47; also builds the neighbour lists)   1 compute_DFSPH_factor (:114-139)
+ *   2 compute_density_change (:157-178)   3 compute_density_adv (:198-205)
+ *   4 compute_density_error (:221-227; arg = offset, out_dev = zero-initialised double accumulator)
+ *   5 multiply_time_step(dfsph_factor, arg) (:229-233)
+ *   6 divergence_solver_iteration_kernel (:278-290)   7 pressure_solve_iteration_kernel (:354-367)
+ *   8 compute_non_pressure_forces (:92-101)   9 predict_velocity (:392-397)   10 advect (:104-111)
+ * The convergence loops (divergence_solve, pressure_solve) stay on the host, as in the reference.
+ * sph_set_dfsph(1) switches the density pass to DFSPH semantics (no clamp, no EOS). */
+int sph_set_dfsph(SphCtx *ctx, int32_t enable);
+int sph_dfsph_op(SphCtx *ctx, int32_t op, float arg, void *out_dev, void *stream);
 
 /* ---- x-slab sharding across the GPUs of one node (new; the reference is single-device) -------
  * One process per GPU.  Each rank owns the cell layers [x_lo, x_hi) of the x axis and keeps

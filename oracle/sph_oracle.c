@@ -29,6 +29,8 @@
  *   WCSPH.py:46-85              compute_pressure_forces
  *   WCSPH.py:88-140             compute_non_pressure_forces
  *   WCSPH.py:143-156            advect / substep
+ *   DFSPH.py:116-227,278-311,354-408  DFSPH factor, density change / adv, error, Jacobi iteration kernels,
+ *                                predict_velocity, advect (simulationMethod 4; host loops live in sph_oracle.py)
  *
  * Conscious, tested deviations from the literal reference (SURVEY.md section 8 Q-list):
  *   Q3  neighbour cells with any axis index out of [0, grid_num) are skipped (the
@@ -82,6 +84,7 @@ typedef struct {
     int32_t *color;                   /* [n][3] */
     int32_t *grid_ids;                /* [n] */
     int32_t *grid_particles_num;      /* [C]; after neighbour build: inclusive prefix sum */
+    REAL *dfsph_factor, *density_adv; /* DFSPH only (particle_system.py:115-117); may be NULL */
 } OracleState;
 
 #define MAT_SOLID 0
@@ -195,6 +198,8 @@ int oracle_neighbor_build(const OracleParams *P, OracleState *S) {
     permute_i32(S->material, dst, n, 1, tmp);
     permute_i32(S->color, dst, n, 3, tmp);
     permute_i32(S->is_dynamic, dst, n, 1, tmp);
+    if (S->dfsph_factor) permute_real(S->dfsph_factor, dst, n, 1, tmp); /* particle_system.py:348-350 */
+    if (S->density_adv) permute_real(S->density_adv, dst, n, 1, tmp);
     free(fill); free(dst); free(tmp);
     return 0;
 }
@@ -502,4 +507,160 @@ int oracle_step(const OracleParams *P, OracleState *S, int n_dyn, const int32_t 
     }
     oracle_enforce_boundary_3D(P, S, MAT_FLUID);
     return 0;
+}
+
+
+/* ==================================================================================== */
+/* DFSPH (reference DFSPH.py, simulationMethod 4).  compute_densities and                */
+/* compute_non_pressure_forces are the WCSPH functions above (DFSPH.py:24-47, 50-101 are  */
+/* the same expressions; the only difference, the reaction of the boundary viscosity, is  */
+/* multiplied by boundary_viscosity = 0.0).                                               */
+/* ==================================================================================== */
+
+/* DFSPH.py:114-154 */
+void oracle_dfsph_compute_factor(const OracleParams *P, OracleState *S) {
+    const int32_t n = P->n;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int32_t p_i = 0; p_i < n; ++p_i) {
+        if (S->material[p_i] != MAT_FLUID) continue;
+        REAL ret[4] = {0, 0, 0, 0};
+        FOR_ALL_NEIGHBORS_BEGIN(P, S, p_i, p_j)
+            REAL gw[3];
+            cubic_kernel_derivative(P, _r, gw);
+            REAL g[3] = {-S->m_V[p_j] * gw[0], -S->m_V[p_j] * gw[1], -S->m_V[p_j] * gw[2]};
+            if (S->material[p_j] == MAT_FLUID) ret[3] += g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+            for (int k = 0; k < 3; ++k) ret[k] -= g[k];
+        FOR_ALL_NEIGHBORS_END
+        REAL sum_grad_p_k = ret[3];
+        sum_grad_p_k += ret[0] * ret[0] + ret[1] * ret[1] + ret[2] * ret[2];
+        S->dfsph_factor[p_i] = (sum_grad_p_k > (REAL)1e-6) ? (REAL)-1.0 / sum_grad_p_k : (REAL)0.0;
+    }
+}
+
+/* DFSPH.py:157-196 (mode 0: compute_density_change) and :198-219 (mode 1: compute_density_adv) */
+void oracle_dfsph_density_change(const OracleParams *P, OracleState *S, int mode) {
+    const int32_t n = P->n;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int32_t p_i = 0; p_i < n; ++p_i) {
+        if (S->material[p_i] != MAT_FLUID) continue;
+        REAL acc = (REAL)0.0;
+        int32_t nn = 0;
+        const REAL *vi = S->v + 3 * (size_t)p_i;
+        FOR_ALL_NEIGHBORS_BEGIN(P, S, p_i, p_j)
+            REAL gw[3];
+            cubic_kernel_derivative(P, _r, gw);
+            const REAL *vj = S->v + 3 * (size_t)p_j;
+            acc += S->m_V[p_j] * ((vi[0] - vj[0]) * gw[0] + (vi[1] - vj[1]) * gw[1] + (vi[2] - vj[2]) * gw[2]);
+            nn += 1;
+        FOR_ALL_NEIGHBORS_END
+        if (mode == 0) {
+            REAL da = acc > (REAL)0.0 ? acc : (REAL)0.0; /* only correct positive divergence */
+            if (nn < 20) da = (REAL)0.0;                 /* particle deficiency (3-D) */
+            S->density_adv[p_i] = da;
+        } else {
+            REAL da = S->density[p_i] / P->density0 + P->dt * acc;
+            S->density_adv[p_i] = da > (REAL)1.0 ? da : (REAL)1.0;
+        }
+    }
+}
+
+/* DFSPH.py:221-227: serial sum in particle order (the reference reduces with atomics) */
+double oracle_dfsph_density_error(const OracleParams *P, const OracleState *S, double offset) {
+    REAL err = (REAL)0.0;
+    for (int32_t i = 0; i < P->n; ++i)
+        if (S->material[i] == MAT_FLUID) err += P->density0 * S->density_adv[i] - (REAL)offset;
+    return (double)err;
+}
+
+/* DFSPH.py:229-233 on dfsph_factor */
+void oracle_dfsph_multiply_factor(const OracleParams *P, OracleState *S, double time_step) {
+    for (int32_t i = 0; i < P->n; ++i)
+        if (S->material[i] == MAT_FLUID) S->dfsph_factor[i] *= (REAL)time_step;
+}
+
+/* DFSPH.py:278-311 (mode 0: divergence_solver_iteration_kernel) and :354-389 (mode 1:
+ * pressure_solve_iteration_kernel).  Reactions on dynamic rigid particles: mode 0 adds them to an
+ * acceleration that compute_non_pressure_forces overwrites before anybody reads it (DFSPH.py:402),
+ * so they are dropped here; mode 1 accumulates them in gather form (deterministic order). */
+void oracle_dfsph_iteration(const OracleParams *P, OracleState *S, int mode) {
+    const int32_t n = P->n;
+    const REAL eps = (REAL)1e-5;
+    const REAL boff = mode == 0 ? (REAL)0.0 : (REAL)1.0;
+    REAL *vnew = (REAL *)malloc(sizeof(REAL) * 3 * (size_t)(n > 0 ? n : 1));
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int32_t p_i = 0; p_i < n; ++p_i) {
+        for (int k = 0; k < 3; ++k) vnew[3 * (size_t)p_i + k] = S->v[3 * (size_t)p_i + k];
+        if (S->material[p_i] != MAT_FLUID) continue;
+        REAL k_i = (S->density_adv[p_i] - boff) * S->dfsph_factor[p_i];
+        REAL dv[3] = {0, 0, 0};
+        REAL *vi = vnew + 3 * (size_t)p_i;
+        FOR_ALL_NEIGHBORS_BEGIN(P, S, p_i, p_j)
+            if (S->material[p_j] == MAT_FLUID) {
+                REAL k_j = (S->density_adv[p_j] - boff) * S->dfsph_factor[p_j];
+                REAL k_sum = k_i + P->density0 / P->density0 * k_j;
+                if (R_FABS(k_sum) > eps) {
+                    REAL gw[3];
+                    cubic_kernel_derivative(P, _r, gw);
+                    for (int k = 0; k < 3; ++k) {
+                        REAL gp = -S->m_V[p_j] * gw[k];
+                        if (mode == 0) dv[k] -= P->dt * k_sum * gp;
+                        else vi[k] -= P->dt * k_sum * gp;
+                    }
+                }
+            } else if (R_FABS(k_i) > eps) {
+                REAL gw[3];
+                cubic_kernel_derivative(P, _r, gw);
+                for (int k = 0; k < 3; ++k) {
+                    REAL gp = -S->m_V[p_j] * gw[k];
+                    REAL vel_change = -P->dt * (REAL)1.0 * k_i * gp;
+                    if (mode == 0) dv[k] += vel_change;
+                    else vi[k] += vel_change;
+                }
+            }
+        FOR_ALL_NEIGHBORS_END
+        if (mode == 0) for (int k = 0; k < 3; ++k) vi[k] += dv[k];
+    }
+    if (mode == 1) { /* reactions, DFSPH.py:388-389 */
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int32_t p_j = 0; p_j < n; ++p_j) {
+            if (!is_dynamic_rigid(S, p_j)) continue;
+            REAL acc[3] = {0, 0, 0};
+            FOR_ALL_NEIGHBORS_BEGIN(P, S, p_j, p_f)
+                if (S->material[p_f] == MAT_FLUID) {
+                    REAL k_f = (S->density_adv[p_f] - boff) * S->dfsph_factor[p_f];
+                    if (R_FABS(k_f) > eps) {
+                        REAL rr[3] = {-_r[0], -_r[1], -_r[2]}; /* x_f - x_rigid */
+                        REAL gw[3];
+                        cubic_kernel_derivative(P, rr, gw);
+                        for (int k = 0; k < 3; ++k) {
+                            REAL gp = -S->m_V[p_j] * gw[k];
+                            REAL vel_change = -P->dt * (REAL)1.0 * k_f * gp;
+                            acc[k] += -vel_change * (REAL)1.0 / P->dt * S->density[p_f] / S->density[p_j];
+                        }
+                    }
+                }
+            FOR_ALL_NEIGHBORS_END
+            for (int k = 0; k < 3; ++k) S->acceleration[3 * (size_t)p_j + k] += acc[k];
+        }
+    }
+    memcpy(S->v, vnew, sizeof(REAL) * 3 * (size_t)n);
+    free(vnew);
+}
+
+/* DFSPH.py:392-397 */
+void oracle_dfsph_predict_velocity(const OracleParams *P, OracleState *S) {
+    for (int32_t p = 0; p < P->n; ++p)
+        if (S->is_dynamic[p] && S->material[p] == MAT_FLUID)
+            for (int k = 0; k < 3; ++k) S->v[3 * (size_t)p + k] += P->dt * S->acceleration[3 * (size_t)p + k];
+}
+
+/* DFSPH.py:104-111 */
+void oracle_dfsph_advect(const OracleParams *P, OracleState *S) {
+    for (int32_t p = 0; p < P->n; ++p) {
+        if (!S->is_dynamic[p]) continue;
+        for (int k = 0; k < 3; ++k) {
+            if (is_dynamic_rigid(S, p)) S->v[3 * (size_t)p + k] += P->dt * S->acceleration[3 * (size_t)p + k];
+            S->x[3 * (size_t)p + k] += P->dt * S->v[3 * (size_t)p + k];
+        }
+    }
 }

@@ -48,7 +48,7 @@ def _params_struct(real):
 class _State(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in (
         "object_id", "x", "x_0", "v", "acceleration", "m_V", "m", "density", "pressure", "material", "is_dynamic",
-        "color", "grid_ids", "grid_particles_num")]
+        "color", "grid_ids", "grid_particles_num", "dfsph_factor", "density_adv")]
 
 
 def _lib(f64: bool):
@@ -59,6 +59,7 @@ def _lib(f64: bool):
         assert lib.oracle_real_bytes() == (8 if f64 else 4)
         lib.oracle_neighbor_build.restype = C.c_int
         lib.oracle_step.restype = C.c_int
+        lib.oracle_dfsph_density_error.restype = C.c_double
         _LIBS[key] = lib
     return _LIBS[key]
 
@@ -90,8 +91,9 @@ class OracleSim:
         self.support_radius = self.particle_radius * 4.0
         self.m_V0 = 0.8 * self.particle_diameter ** self.dim
         self.grid_num = np.ceil(self.domain_size / self.support_radius).astype(int)
-        if config.get_cfg("simulationMethod") != 0:
-            raise NotImplementedError("oracle restates WCSPH (simulationMethod 0) only")
+        self.method = config.get_cfg("simulationMethod")
+        if self.method not in (0, 4):
+            raise NotImplementedError("oracle restates WCSPH (0) and DFSPH (4) only")
 
         arrays, self.object_collection, self.object_id_rigid_body, counts = assemble_particles(
             config, self.dim, self.particle_diameter)
@@ -114,6 +116,8 @@ class OracleSim:
         self.grid_ids = np.zeros(n, np.int32)
         self.C = int(np.prod(self.grid_num))
         self.grid_particles_num = np.zeros(self.C, np.int32)
+        self.dfsph_factor = np.zeros(n, r)
+        self.density_adv = np.zeros(n, r)
 
         h = self.support_radius
         k = 8 / np.pi / h ** self.dim
@@ -142,6 +146,9 @@ class OracleSim:
     def _state(self):
         s = _State()
         for k, _ in _State._fields_:
+            if k in ("dfsph_factor", "density_adv") and self.method != 4:
+                setattr(s, k, None)
+                continue
             a = getattr(self, k)
             assert a.flags["C_CONTIGUOUS"]
             setattr(s, k, a.ctypes.data)
@@ -197,12 +204,105 @@ class OracleSim:
         return np.array(R[:], dtype=self.real).reshape(3, 3)
 
     def substep(self):
+        if self.method == 4:
+            return self.dfsph_substep()
         self.compute_densities()
         self.compute_non_pressure_forces()
         self.compute_pressure_forces()
         self.advect()
 
+    # -- DFSPH (DFSPH.py; host loops restated from :236-276 and :314-352) -------------------------
+    m_max_iterations_v = 100
+    m_max_iterations = 100
+    max_error_V = 0.1
+    max_error = 0.05
+
+    def compute_DFSPH_factor(self):
+        self._call("oracle_dfsph_compute_factor")
+
+    def compute_density_change(self):
+        self._call("oracle_dfsph_density_change", C.c_int(0))
+
+    def compute_density_adv(self):
+        self._call("oracle_dfsph_density_change", C.c_int(1))
+
+    def compute_density_error(self, offset):
+        return float(self._call("oracle_dfsph_density_error", C.c_double(offset)))
+
+    def multiply_time_step_factor(self, ts):
+        self._call("oracle_dfsph_multiply_factor", C.c_double(ts))
+
+    def divergence_solver_iteration_kernel(self):
+        self._call("oracle_dfsph_iteration", C.c_int(0))
+
+    def pressure_solve_iteration_kernel(self):
+        self._call("oracle_dfsph_iteration", C.c_int(1))
+
+    def predict_velocity(self):
+        self._call("oracle_dfsph_predict_velocity")
+
+    def dfsph_advect(self):
+        self._call("oracle_dfsph_advect")
+
+    def divergence_solve(self):
+        dt = float(self.P.dt)
+        rho0 = float(self.P.density0)
+        n_fluid = int((self.material == 1).sum())
+        self.compute_density_change()
+        self.multiply_time_step_factor(1 / dt)
+        it = 0
+        avg = 0.0
+        while it < 1 or it < self.m_max_iterations_v:
+            self.divergence_solver_iteration_kernel()
+            self.compute_density_change()
+            avg = self.compute_density_error(0.0) / n_fluid
+            eta = 1.0 / dt * self.max_error_V * 0.01 * rho0
+            if avg <= eta:
+                break
+            it += 1
+        self.multiply_time_step_factor(dt)
+        self.last_iterations_v, self.last_err_v = it, avg
+        return it
+
+    def pressure_solve(self):
+        dt = float(self.P.dt)
+        rho0 = float(self.P.density0)
+        n_fluid = int((self.material == 1).sum())
+        self.compute_density_adv()
+        self.multiply_time_step_factor(1 / (dt * dt))
+        it = 0
+        avg = 0.0
+        while it < 1 or it < self.m_max_iterations:
+            self.pressure_solve_iteration_kernel()
+            self.compute_density_adv()
+            avg = self.compute_density_error(rho0) / n_fluid
+            eta = self.max_error * 0.01 * rho0
+            if avg <= eta:
+                break
+            it += 1
+        self.last_iterations, self.last_err = it, avg
+        return it
+
+    def dfsph_substep(self):
+        self.compute_densities()
+        self.compute_DFSPH_factor()
+        self.divergence_solve()
+        self.compute_non_pressure_forces()
+        self.predict_velocity()
+        self.pressure_solve()
+        self.dfsph_advect()
+
     def step(self):
+        if self.method == 4:
+            # sph_base.py:263-271 with the DFSPH substep
+            self.initialize_particle_system()
+            self.compute_moving_boundary_volume()
+            self.dfsph_substep()
+            for oid in self.dyn_ids:
+                self.solve_constraints(oid)
+                self.enforce_boundary_3D(0)
+            self.enforce_boundary_3D(1)
+            return
         ids = (C.c_int32 * max(1, len(self.dyn_ids)))(*self.dyn_ids)
         rc = (self.creal * max(3, 3 * len(self.dyn_ids)))()
         for b, oid in enumerate(self.dyn_ids):

@@ -1,0 +1,131 @@
+"""``DFSPHSolver`` (reference ``DFSPH.py:5-408``, simulationMethod 4): divergence-free SPH.
+
+Same method names, constants and host-side convergence loops as the reference; every kernel is one
+``sph_dfsph_op`` call on the CUDA engine (``csrc/sph_dfsph.cuh``).  The density pass builds the
+per-step neighbour lists that all DFSPH kernels walk.
+"""
+from __future__ import annotations
+
+import torch
+
+from .sph_base import SPHBase
+
+(OP_DENSITIES, OP_FACTOR, OP_DENSITY_CHANGE, OP_DENSITY_ADV, OP_DENSITY_ERROR, OP_MULTIPLY_FACTOR,
+ OP_DIVERGENCE_ITERATION, OP_PRESSURE_ITERATION, OP_NON_PRESSURE, OP_PREDICT_VELOCITY, OP_ADVECT) = range(11)
+
+
+class DFSPHSolver(SPHBase):
+    def __init__(self, particle_system):
+        super().__init__(particle_system)
+        self.surface_tension = 0.01
+        self.dt[None] = self.ps.cfg.get_cfg("timeStepSize")
+        self.enable_divergence_solver = True
+        self.m_max_iterations_v = 100
+        self.m_max_iterations = 100
+        self.m_eps = 1e-5
+        self.max_error_V = 0.1
+        self.max_error = 0.05
+        self.verbose = False
+        self.last_iterations_v = 0
+        self.last_iterations = 0
+        self.ps._engine.set_dfsph(True)
+        self._err = torch.zeros(1, dtype=torch.float64, device=self.ps.device)
+
+    def _op(self, op, arg=0.0, out=None):
+        self.ps._push()
+        self.ps._engine.dfsph_op(op, arg, out)
+        self.ps._after_engine()
+
+    # ---- kernels (DFSPH.py names) ------------------------------------------------------------
+    def compute_densities(self):
+        self._op(OP_DENSITIES)
+
+    def compute_DFSPH_factor(self):
+        self._op(OP_FACTOR)
+
+    def compute_density_change(self):
+        self._op(OP_DENSITY_CHANGE)
+
+    def compute_density_adv(self):
+        self._op(OP_DENSITY_ADV)
+
+    def compute_density_error(self, offset):
+        self._err.zero_()
+        self._op(OP_DENSITY_ERROR, offset, self._err)
+        return float(self._err.item())  # host sync, like the reference's kernel return value
+
+    def multiply_time_step(self, field, time_step):
+        if field is not self.ps.dfsph_factor:
+            raise NotImplementedError("the reference only ever scales dfsph_factor")
+        self._op(OP_MULTIPLY_FACTOR, time_step)
+
+    def divergence_solver_iteration_kernel(self):
+        self._op(OP_DIVERGENCE_ITERATION)
+
+    def pressure_solve_iteration_kernel(self):
+        self._op(OP_PRESSURE_ITERATION)
+
+    def compute_non_pressure_forces(self):
+        self._op(OP_NON_PRESSURE)
+
+    def predict_velocity(self):
+        self._op(OP_PREDICT_VELOCITY)
+
+    def advect(self):
+        self._op(OP_ADVECT)
+
+    # ---- host loops (DFSPH.py:236-276, 314-352) -----------------------------------------------
+    def divergence_solver_iteration(self):
+        self.divergence_solver_iteration_kernel()
+        self.compute_density_change()
+        density_err = self.compute_density_error(0.0)
+        return density_err / self.ps.fluid_particle_num
+
+    def divergence_solve(self):
+        self.compute_density_change()
+        inv_dt = 1 / self.dt[None]
+        self.multiply_time_step(self.ps.dfsph_factor, inv_dt)
+        m_iterations_v = 0
+        avg_density_err = 0.0
+        while m_iterations_v < 1 or m_iterations_v < self.m_max_iterations_v:
+            avg_density_err = self.divergence_solver_iteration()
+            eta = 1.0 / self.dt[None] * self.max_error_V * 0.01 * self.density_0
+            if avg_density_err <= eta:
+                break
+            m_iterations_v += 1
+        if self.verbose:
+            print(f"DFSPH - iteration V: {m_iterations_v} Avg density err: {avg_density_err}")
+        self.multiply_time_step(self.ps.dfsph_factor, self.dt[None])
+        self.last_iterations_v = m_iterations_v
+
+    def pressure_solve_iteration(self):
+        self.pressure_solve_iteration_kernel()
+        self.compute_density_adv()
+        density_err = self.compute_density_error(self.density_0)
+        return density_err / self.ps.fluid_particle_num
+
+    def pressure_solve(self):
+        inv_dt2 = 1 / (self.dt[None] * self.dt[None])
+        self.compute_density_adv()
+        self.multiply_time_step(self.ps.dfsph_factor, inv_dt2)
+        m_iterations = 0
+        avg_density_err = 0.0
+        while m_iterations < 1 or m_iterations < self.m_max_iterations:
+            avg_density_err = self.pressure_solve_iteration()
+            eta = self.max_error * 0.01 * self.density_0
+            if avg_density_err <= eta:
+                break
+            m_iterations += 1
+        if self.verbose:
+            print(f"DFSPH - iterations: {m_iterations} Avg density Err: {avg_density_err:.4f}")
+        self.last_iterations = m_iterations
+
+    def substep(self):
+        self.compute_densities()
+        self.compute_DFSPH_factor()
+        if self.enable_divergence_solver:
+            self.divergence_solve()
+        self.compute_non_pressure_forces()
+        self.predict_velocity()
+        self.pressure_solve()
+        self.advect()

@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "sph_advect", "sph_enforce_boundary", "sph_set_rigid_bodies", "sph_compute_com", "sph_compute_rigid_rest_cm",
     "sph_solve_constraints", "sph_step", "sph_read_status", "sph_clear_status", "sph_particle_count",
     "sph_launch_count", "sph_profile_step", "sph_timer_name", "sph_slab_configure", "sph_slab_set_counts",
-    "sph_state_offsets", "sph_slab_step", "sph_slab_compute", "sph_slab_pair_times",
+    "sph_state_offsets", "sph_slab_step", "sph_slab_compute", "sph_slab_pair_times", "sph_set_dfsph", "sph_dfsph_op",
 ]
 
 
@@ -61,7 +61,7 @@ class SphParams(C.Structure):
 class SphFields(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in (
         "object_id", "x", "x_0", "v", "acceleration", "m_V", "m", "density", "pressure", "material", "is_dynamic",
-        "color", "grid_ids", "solid_id")]
+        "color", "grid_ids", "solid_id", "dfsph_factor", "density_adv")]
 
 
 class SphRigidBody(C.Structure):
@@ -124,6 +124,8 @@ def load():
         "sph_state_offsets": (C.c_int, [vp, C.POINTER(u64)]),
         "sph_slab_step": (C.c_int, [vp, vp, i32, vp]),
         "sph_slab_compute": (C.c_int, [vp, vp]),
+        "sph_set_dfsph": (C.c_int, [vp, i32]),
+        "sph_dfsph_op": (C.c_int, [vp, i32, C.c_float, vp, vp]),
         "sph_slab_pair_times": (C.c_int, [vp, i32, C.POINTER(C.c_float)]),
     }
     for name, (res, args) in sig.items():

@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 
-#include "sph_kernels.cuh"
+#include "sph_dfsph.cuh"
 
 namespace {
 
@@ -25,7 +25,7 @@ enum { T_ZERO, T_HASH, T_SCAN, T_BUCKET, T_MOVE, T_BVOL, T_DENSITY, T_FORCE, T_A
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
-    uint64_t off_state[13];  // posm, veld, x0id, misc, acc (x2), aux, fpos, fvel
+    uint64_t off_state[14];  // posm, veld, x0id, misc, acc (x2), aux, fpos, fvel, dfs
     uint64_t off_cid, off_grid_ids, off_perm, off_ticket;
     uint64_t off_zero_begin, off_tile_counter, off_tile_state, off_cell_end, off_zero_end;
     uint64_t off_solid_slot, off_status, off_bodies, off_scratch, off_nbr_list, off_nbr_cnt;
@@ -39,7 +39,7 @@ Layout make_layout(int64_t n_max, int64_t C, int64_t n_solid, int n_bodies) {
     uint64_t o = 0;
     auto take = [&](uint64_t bytes) { uint64_t r = o; o = align_up(o + bytes, 256); return r; };
     uint64_t n = (uint64_t)(n_max > 0 ? n_max : 1);
-    for (int k = 0; k < 13; ++k) L.off_state[k] = take(n * sizeof(float4));
+    for (int k = 0; k < 14; ++k) L.off_state[k] = take(n * sizeof(float4));
     L.off_cid = take(n * 4);
     L.off_grid_ids = take(n * 4);
     L.off_perm = take(n * 4);
@@ -89,6 +89,7 @@ struct SphCtx {
     cudaEvent_t pair_ev[3] = {nullptr, nullptr, nullptr};
     cudaStream_t capture_stream = nullptr;  // graphs are captured here (the legacy stream cannot capture)
     bool built = false;  // neighbour structure valid for current positions
+    bool list_valid = false;  // neighbour lists valid for current positions (DFSPH kernels)
 };
 
 namespace {
@@ -121,7 +122,14 @@ void derive_params(SphCtx *c) {
     DevParams &P = c->P;
     P.gx = h.grid_num[0]; P.gy = h.grid_num[1]; P.gz = h.grid_num[2];
     P.C = P.gx * P.gy * P.gz;
-    P.h = h.h; P.h2 = h.h * h.h; P.inv_h = 1.0f / h.h; P.d2 = h.diameter * h.diameter;
+    P.h = h.h; P.inv_h = 1.0f / h.h; P.d2 = h.diameter * h.diameter;
+    {   // h2 = min{t : sqrtf(t) >= h}: then r2 < h2 <=> sqrtf(r2) < h, the reference's predicate, exactly
+        float t = h.h * h.h;
+        while (std::sqrt(t) >= h.h) t = std::nextafter(t, 0.0f);
+        while (std::sqrt(std::nextafter(t, INFINITY)) < h.h) t = std::nextafter(t, INFINITY);
+        P.h2 = std::nextafter(t, INFINITY);
+        P.h2_scan = P.h2 * 1.000002f;  // FFMA-chain prefilter: a superset of the exact hits
+    }
     P.m_V0 = h.m_V0; P.rho0 = h.density0; P.inv_rho0sq = 1.0f / (h.density0 * h.density0);
     P.stiffness = h.stiffness; P.exponent = h.exponent;
     float er = std::round(h.exponent);
@@ -142,8 +150,8 @@ void bind_arrays(SphCtx *c) {
     char *w = c->ws;
     const Layout &L = c->L;
     DevArrays &S = c->S;
-    float4 *st[13];
-    for (int k = 0; k < 13; ++k) st[k] = reinterpret_cast<float4 *>(w + L.off_state[k]);
+    float4 *st[14];
+    for (int k = 0; k < 14; ++k) st[k] = reinterpret_cast<float4 *>(w + L.off_state[k]);
     int p = c->parity;
     S.posm = st[0 + 5 * p]; S.veld = st[1 + 5 * p]; S.x0id = st[2 + 5 * p]; S.misc = st[3 + 5 * p]; S.acc = st[4 + 5 * p];
     int q = 1 - p;
@@ -151,6 +159,7 @@ void bind_arrays(SphCtx *c) {
     S.aux = st[10];
     S.fpos = st[11];
     S.fvel = st[12];
+    S.dfs = st[13];
     S.cid = reinterpret_cast<int32_t *>(w + L.off_cid);
     S.grid_ids = reinterpret_cast<int32_t *>(w + L.off_grid_ids);
     S.perm = reinterpret_cast<int32_t *>(w + L.off_perm);
@@ -280,7 +289,7 @@ int launch_step(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels) {
     if (!c->bodies.empty()) { rc = launch_rigid_solve(c, st, kernels); if (rc) return rc; }
     if (tm) tm->mark(T_TOTAL);
     CUDA_TRY(c, cudaGetLastError());
-    c->built = false;  // positions moved
+    c->built = false; c->list_valid = false;  // positions moved
     return SPH_OK;
 }
 
@@ -371,7 +380,7 @@ int sph_pack(SphCtx *ctx, const SphFields *f, int64_t n, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ctx->P.n = (int32_t)n;
     drop_graphs(ctx);
-    ctx->built = false;
+    ctx->built = false; ctx->list_valid = false;
     if (n == 0) return SPH_OK;
     k_pack<<<blocks_for(n, 256), 256, 0, st>>>(ctx->P, ctx->S, *f);
     ctx->launches += 1;
@@ -420,7 +429,7 @@ int sph_upload_xv(SphCtx *ctx, const float *x, const float *v, void *stream) {
     if (ctx->P.n == 0) return SPH_OK;
     k_upload_xv<<<blocks_for(ctx->P.n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S, x, v);
     ctx->launches += 1;
-    ctx->built = false;
+    ctx->built = false; ctx->list_valid = false;
     CUDA_TRY(ctx, cudaGetLastError());
     return SPH_OK;
 }
@@ -480,7 +489,7 @@ int sph_advect(SphCtx *ctx, void *stream) {
     if (ctx->P.n == 0) return SPH_OK;
     k_advect<false><<<blocks_for(ctx->P.n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S);
     ctx->launches += 1;
-    ctx->built = false;
+    ctx->built = false; ctx->list_valid = false;
     CUDA_TRY(ctx, cudaGetLastError());
     return SPH_OK;
 }
@@ -490,7 +499,7 @@ int sph_enforce_boundary(SphCtx *ctx, int32_t particle_type, void *stream) {
     if (ctx->P.n == 0) return SPH_OK;
     k_enforce_boundary<<<blocks_for(ctx->P.n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S, particle_type);
     ctx->launches += 1;
-    ctx->built = false;
+    ctx->built = false; ctx->list_valid = false;
     CUDA_TRY(ctx, cudaGetLastError());
     return SPH_OK;
 }
@@ -520,7 +529,7 @@ static int rigid_call(SphCtx *ctx, int32_t body, int mode, float *out, void *str
     if (body < 0 || body >= (int)ctx->bodies.size()) return fail(ctx, SPH_E_ARG, "rigid body index out of range");
     k_rigid<<<1, RIGID_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S, dev_bodies(ctx), body, mode, out);
     ctx->launches += 1;
-    if (mode == 2) ctx->built = false;
+    if (mode == 2) ctx->built = false; ctx->list_valid = false;
     CUDA_TRY(ctx, cudaGetLastError());
     return SPH_OK;
 }
@@ -576,7 +585,7 @@ int sph_step(SphCtx *ctx, int32_t nsteps, void *stream) {
         CUDA_TRY(ctx, cudaGraphLaunch(*slot, st));
         ctx->launches += *kslot;
         if (span & 1) { ctx->parity = par ^ 1; bind_arrays(ctx); }
-        ctx->built = false;
+        ctx->built = false; ctx->list_valid = false;
         s += span;
     }
     return SPH_OK;
@@ -649,7 +658,7 @@ int sph_slab_compute(SphCtx *ctx, void *stream) {
         launch_pair_density(ctx, st, &ctx->launches);
         launch_pair_force_and_advect(ctx, st, nullptr, &ctx->launches);
     }
-    ctx->built = false;
+    ctx->built = false; ctx->list_valid = false;
     CUDA_TRY(ctx, cudaGetLastError());
     return SPH_OK;
 }
@@ -664,6 +673,55 @@ int sph_slab_pair_times(SphCtx *ctx, int32_t enable, float *ms_out) {
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms_out[1], ctx->pair_ev[1], ctx->pair_ev[2]));
     }
     ctx->time_pair = enable != 0;
+    return SPH_OK;
+}
+
+int sph_set_dfsph(SphCtx *ctx, int32_t enable) {
+    if (!ctx) return SPH_E_ARG;
+    ctx->P.dfsph = enable ? 1 : 0;
+    drop_graphs(ctx);
+    return SPH_OK;
+}
+
+int sph_dfsph_op(SphCtx *ctx, int32_t op, float arg, void *out_dev, void *stream) {
+    if (!ctx) return SPH_E_ARG;
+    if (!ctx->P.dfsph) return fail(ctx, SPH_E_ARG, "sph_set_dfsph(1) was not called");
+    const DevParams &P = ctx->P;
+    if (P.n == 0) return SPH_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int b128 = blocks_for(P.n, 128), b256 = blocks_for(P.n, 256);
+    if (op >= DFSPH_COMPUTE_DENSITIES && op <= DFSPH_NON_PRESSURE_FORCES && op != DFSPH_DENSITY_ERROR &&
+        op != DFSPH_MULTIPLY_FACTOR) {
+        if (!ctx->built)
+            return fail(ctx, SPH_E_ARG, "neighbour structure is stale: call sph_neighbor_build first");
+        if (op != DFSPH_COMPUTE_DENSITIES && !ctx->list_valid)
+            return fail(ctx, SPH_E_ARG, "neighbour lists are stale: run op 0 (compute_densities) first");
+    }
+    switch (op) {
+        case DFSPH_COMPUTE_DENSITIES:
+            launch_pair_density(ctx, st, &ctx->launches);
+            ctx->list_valid = true;
+            break;
+        case DFSPH_COMPUTE_FACTOR: k_dfsph_factor<<<b128, 128, 0, st>>>(P, ctx->S); break;
+        case DFSPH_DENSITY_CHANGE: k_dfsph_density_change<0><<<b128, 128, 0, st>>>(P, ctx->S); break;
+        case DFSPH_DENSITY_ADV: k_dfsph_density_change<1><<<b128, 128, 0, st>>>(P, ctx->S); break;
+        case DFSPH_DENSITY_ERROR:
+            if (!out_dev) return SPH_E_ARG;
+            k_dfsph_density_error<<<b256, 256, 0, st>>>(P, ctx->S, arg, static_cast<double *>(out_dev));
+            break;
+        case DFSPH_MULTIPLY_FACTOR: k_dfsph_multiply_factor<<<b256, 256, 0, st>>>(P, ctx->S, arg); break;
+        case DFSPH_DIVERGENCE_ITERATION: k_dfsph_iteration<0><<<b128, 128, 0, st>>>(P, ctx->S); break;
+        case DFSPH_PRESSURE_ITERATION: k_dfsph_iteration<1><<<b128, 128, 0, st>>>(P, ctx->S); break;
+        case DFSPH_NON_PRESSURE_FORCES: k_dfsph_non_pressure<<<b128, 128, 0, st>>>(P, ctx->S); break;
+        case DFSPH_PREDICT_VELOCITY: k_dfsph_predict_velocity<<<b256, 256, 0, st>>>(P, ctx->S); break;
+        case DFSPH_ADVECT:
+            k_dfsph_advect<<<b256, 256, 0, st>>>(P, ctx->S);
+            ctx->built = false; ctx->list_valid = false;
+            break;
+        default: return fail(ctx, SPH_E_ARG, "unknown DFSPH op");
+    }
+    if (op != DFSPH_COMPUTE_DENSITIES) ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
     return SPH_OK;
 }
 

@@ -26,7 +26,7 @@ struct DevParams {
     int32_t n_solid;
     int32_t C;
     int32_t gx, gy, gz;
-    float h, h2, inv_h, d2;
+    float h, h2, h2_scan, inv_h, d2;  // h2: r2 < h2 <=> sqrtf(r2) < h exactly; h2_scan: conservative prefilter
     float m_V0, rho0, inv_rho0sq, stiffness, exponent;
     int32_t exponent_int;  // >0: exponent is that small integer (multiply chain), else powf
     float sigma, d_visc, visc_eps, dt;
@@ -40,6 +40,7 @@ struct DevParams {
     // express with a single fluid density): the force pass then needs only 2 x 16 B per neighbour
     int32_t uniform_fluid;
     float fluid_m, fluid_mV;
+    int32_t dfsph;  // simulationMethod 4: the density pass neither clamps nor evaluates the EOS
 };
 
 struct DevArrays {
@@ -50,6 +51,7 @@ struct DevArrays {
     //   fpos = {x, y, z, fluid: m/rho_unclamped | solid: m_V}
     //   fvel = {vx, vy, vz, fluid: p/rho^2 (>= 0) | solid: -body density (dynamic) or -inf (static)}
     float4 *fpos, *fvel;
+    float4 *dfs;  // DFSPH: {dfsph_factor, density_adv, -, -} (particle_system.py:115-117)
     int32_t *cid;       // cell id per particle in pre-sort order
     int32_t *grid_ids;  // cell id per particle in sorted order (public grid_ids)
     int32_t *perm;      // bucket slot -> pre-sort index
@@ -69,6 +71,14 @@ struct DevArrays {
 
 constexpr int NBR_CAP = 64;
 constexpr int NBR_OVERFLOW = 0x7fffffff;
+
+// |r|^2 in the reference's (and the oracle's) rounding sequence: three products, two sums, no FMA
+// contraction.  With P.h2 this makes the neighbour predicate `(x_i - x_j).norm() < h`
+// (particle_system.py:384) bit-exact, which matters on lattices where many pairs sit at r == h and
+// DFSPH counts neighbours (DFSPH.py:171-176).
+__device__ __forceinline__ float exact_r2(float rx, float ry, float rz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+}
 
 // r = sqrt(r2) and 1/r from one MUFU.RSQ (|rel err| ~ 1e-7); exact 0 for coincident particles
 __device__ __forceinline__ void fast_norm(float r2, float &r, float &inv_r) {
@@ -161,7 +171,7 @@ __device__ __forceinline__ void for_all_neighbors(const DevParams &P, const floa
             for (int j = j0; j < j1; ++j) {
                 float4 pj = __ldg(posm + j);
                 float rx = xi - pj.x, ry = yi - pj.y, rz = zi - pj.z;
-                float r2 = rx * rx + ry * ry + rz * rz;
+                float r2 = exact_r2(rx, ry, rz);
                 if (r2 < P.h2 && j != i) fn(j, rx, ry, rz, r2, pj);
             }
         }

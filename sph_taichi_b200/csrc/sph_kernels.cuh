@@ -38,6 +38,8 @@ __global__ void k_unpack(DevParams P, DevArrays S, SphFields F) {
     F.acceleration[3 * i] = e.x; F.acceleration[3 * i + 1] = e.y; F.acceleration[3 * i + 2] = e.z;
     if (F.grid_ids) F.grid_ids[i] = S.grid_ids[i];
     if (F.solid_id) F.solid_id[i] = __float_as_int(d.w);
+    if (F.dfsph_factor) F.dfsph_factor[i] = S.dfs[i].x;
+    if (F.density_adv) F.density_adv[i] = S.dfs[i].y;
 }
 
 __global__ void k_unpack_xv(DevParams P, DevArrays S, float *x, float *v, int32_t *object_id) {
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(128) k_boundary_volume(DevParams P, DevArrays 
             for (int j = j0 + lane; j < j1; j += 32) {
                 float4 pj = __ldg(S.posm + j);
                 float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-                float r2 = rx * rx + ry * ry + rz * rz;
+                float r2 = exact_r2(rx, ry, rz);
                 if (r2 < P.h2 && j != i) {
                     uint32_t fj = __float_as_uint(__ldg(&S.misc[j].z));
                     if (!(fj & FLAG_FLUID)) part += w_cubic(P, sqrtf(r2));
@@ -719,7 +721,7 @@ __device__ __forceinline__ uint32_t scan_chunk(const DevParams &P, const float4 
             for (int u = g * 8; u < g * 8 + 8; ++u) {
                 float4 pj = FROM_SMEM ? src[jb + u] : __ldg(src + min(jb + u, j_last));
                 float rx = xi - pj.x, ry = yi - pj.y, rz = zi - pj.z;
-                float d = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, -P.h2)));
+                float d = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, -P.h2_scan)));  // conservative prefilter
                 m = __funnelshift_l(__float_as_uint(d), m, 1);
             }
             done = g * 8 + 8;
@@ -754,7 +756,7 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
         bool dyn = (fl & FLAG_DYNAMIC) != 0;
         float4 vb = S.veld[i];
         S.aux[i] = make_float4(vb.w, 0.0f, dyn ? -2.0f : -1.0f, 0.0f);
-        S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!P.dfsph) S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
         S.nbr_cnt[i] = 0;
         if (P.uniform_fluid) {
             S.fpos[i] = pi;  // w = m_V of the boundary particle
@@ -804,16 +806,18 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
             int hb = 31 - __clz(m);  // highest set bit = earliest candidate: keeps the reference order
             m &= ~(1u << hb);
             int b = len - 1 - hb;
-            S.nbr_list[widx] = jb + b;  // beyond NBR_CAP the last row is overwritten (flagged below)
-            widx = min(widx + (uint32_t)S.npad, widx_cap);
-            ++cnt;
-            if (INLINE_W) {
-                float4 pj = smem ? src[jb + b] : __ldg(src + jb + b);
-                float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-                float r2 = rx * rx + ry * ry + rz * rz;
-                float r, inv_r;
-                fast_norm(r2, r, inv_r);
-                den += pj.w * w_cubic(P, r);
+            float4 pj = smem ? src[jb + b] : __ldg(src + jb + b);
+            float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+            float r2 = exact_r2(rx, ry, rz);
+            if (r2 < P.h2) {  // the exact `norm() < h` of the reference; the scan only pre-filters
+                S.nbr_list[widx] = jb + b;  // beyond NBR_CAP the last row is overwritten (flagged below)
+                widx = min(widx + (uint32_t)S.npad, widx_cap);
+                ++cnt;
+                if (INLINE_W) {
+                    float r, inv_r;
+                    fast_norm(r2, r, inv_r);
+                    den += pj.w * w_cubic(P, r);
+                }
             }
         }
     };
@@ -882,6 +886,11 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
     rho += den;
     rho *= P.rho0;
     float vol = mi.x / rho;  // m_j / rho_j with the UNCLAMPED density (viscosity)
+    if (P.dfsph) {  // DFSPH.py:39-47: plain density, no clamp, no EOS
+        reinterpret_cast<float *>(S.veld + i)[3] = rho;
+        S.aux[i] = make_float4(vol, 0.0f, mi.x, 0.0f);
+        return;
+    }
     float rc = fmaxf(rho, P.rho0);
     float p = tait_pressure(P, rc);
     float dp = p / (rc * rc);

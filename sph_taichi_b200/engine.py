@@ -178,6 +178,13 @@ class Engine:
                     "sph_solve_constraints")
         return out.view(3, 3)
 
+    def set_dfsph(self, enable=True):
+        self._check(self.lib.sph_set_dfsph(self.ctx, int(bool(enable))), "sph_set_dfsph")
+
+    def dfsph_op(self, op, arg=0.0, out=None):
+        self._check(self.lib.sph_dfsph_op(self.ctx, int(op), float(arg), None if out is None else out.data_ptr(),
+                                          self._stream()), "sph_dfsph_op")
+
     def step(self, nsteps=1):
         self._check(self.lib.sph_step(self.ctx, int(nsteps), self._stream()), "sph_step")
 

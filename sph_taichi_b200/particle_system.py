@@ -92,6 +92,11 @@ class ParticleSystem:
         self._t["solid_id"] = torch.full((n,), -1, dtype=torch.int32, device=dev)
         C = int(self.grid_num[0] * self.grid_num[1] * self.grid_num[2])
         self._t["grid_particles_num"] = torch.zeros(C, dtype=torch.int32, device=dev)
+        if self.simulation_method == 4:  # particle_system.py:115-117
+            self._t["dfsph_factor"] = torch.zeros(n, dtype=torch.float32, device=dev)
+            self._t["density_adv"] = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.dfsph_factor = Field(self, self._t["dfsph_factor"], "dfsph_factor", derived=True)
+            self.density_adv = Field(self, self._t["density_adv"], "density_adv", derived=True)
         for k in _PACKED:
             setattr(self, k, Field(self, self._t[k], k))
         self.grid_ids = Field(self, self._t["grid_ids"], "grid_ids", derived=True)
@@ -201,6 +206,9 @@ class ParticleSystem:
         if solver_type == 0:
             from .WCSPH import WCSPHSolver
             return WCSPHSolver(self)
+        if solver_type == 4:
+            from .DFSPH import DFSPHSolver
+            return DFSPHSolver(self)
         raise NotImplementedError(f"Solver type {solver_type} has not been implemented.")
 
     def add_particles(self, object_id, new_particles_num, new_particles_positions, new_particles_velocity,

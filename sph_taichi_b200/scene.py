@@ -149,10 +149,32 @@ def box_16m():
     return dam_break_box([400, 100, 400], domain_end=[16.08, 3.0, 8.08], start=[0.04, 0.04, 0.04])
 
 
+def _as_dfsph(sc, dt=0.004):
+    sc["Configuration"]["simulationMethod"] = 4
+    sc["Configuration"]["timeStepSize"] = dt
+    return sc
+
+
+def dragon_bath_dfsph():
+    """The reference's dragon_bath_dfsph.json: same geometry, DFSPH, dt = 4e-3."""
+    return _as_dfsph(dragon_bath())
+
+
+def high_fluid_dfsph():
+    return _as_dfsph(high_fluid_wcsph())
+
+
+def armadillo_bath_dynamic_dfsph():
+    return _as_dfsph(armadillo_bath_dynamic())
+
+
 NAMED_SCENES = {
     "dragon_bath": dragon_bath,
     "armadillo_bath_dynamic": armadillo_bath_dynamic,
     "high_fluid_wcsph": high_fluid_wcsph,
+    "dragon_bath_dfsph": dragon_bath_dfsph,
+    "high_fluid_dfsph": high_fluid_dfsph,
+    "armadillo_bath_dynamic_dfsph": armadillo_bath_dynamic_dfsph,
     "cube_8k": cube_8k,
     "box_4m": box_4m,
     "box_16m": box_16m,
