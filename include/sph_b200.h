@@ -138,6 +138,9 @@ int sph_compute_com(SphCtx *ctx, int32_t body_index, float *out_dev, void *strea
 int sph_compute_rigid_rest_cm(SphCtx *ctx, int32_t body_index, void *stream);
 /* solve_constraints (sph_base.py:200-222): shape matching; R (row-major 3x3) -> R_out_dev (may be NULL) */
 int sph_solve_constraints(SphCtx *ctx, int32_t body_index, float *R_out_dev, void *stream);
+/* R (row-major 3x3) and centre of mass of the body's last solve (also inside sph_step): 12 floats;
+ * what the reference returns to the host for the OBJ export (sph_base.py:251-257) */
+int sph_get_rigid_state(SphCtx *ctx, int32_t body_index, float *out_dev12, void *stream);
 
 /* ---- SPHBase.step (sph_base.py:263-271) + WCSPHSolver.substep (WCSPH.py:152-156) ---------- */
 /* nsteps whole steps with the fused kernels, replayed from a CUDA graph. */

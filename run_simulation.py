@@ -35,8 +35,9 @@ if __name__ == "__main__":
     substeps = config.get_cfg("numberOfStepsPerRenderUpdate")
     output_interval = int(0.016 / config.get_cfg("timeStepSize"))
     output_ply = config.get_cfg("exportPly")
+    output_obj = config.get_cfg("exportObj")
     series_prefix = "{}_output/particle_object_{}.ply".format(scene_name, "{}")
-    if output_ply:
+    if output_ply or output_obj:
         os.makedirs(f"{scene_name}_output", exist_ok=True)
 
     ps = ParticleSystem(config, GGUI=False)
@@ -51,6 +52,19 @@ if __name__ == "__main__":
         if cnt % output_interval == 0 and output_ply:
             obj_data = ps.dump(obj_id=0)
             write_ply_ascii(series_prefix.format(0).replace(".ply", f"_{cnt_ply:06}.ply"), obj_data["position"])
+        if cnt % output_interval == 0 and output_obj:
+            # posed rigid meshes (reference run_simulation.py:108-111); needs the mesh files on disk
+            for r_body_id in ps.object_id_rigid_body:
+                obj = ps.object_collection[r_body_id]
+                if "meshFaces" not in obj:
+                    continue
+                verts = obj.get("meshVertices", obj["restPosition"])
+                with open(f"{scene_name}_output/obj_{r_body_id}_{cnt_ply:06}.obj", "w") as f:
+                    for v in verts:
+                        f.write(f"v {v[0]:.7g} {v[1]:.7g} {v[2]:.7g}\n")
+                    for t in obj["meshFaces"]:
+                        f.write(f"f {t[0] + 1} {t[1] + 1} {t[2] + 1}\n")
+        if cnt % output_interval == 0 and (output_ply or output_obj):
             cnt_ply += 1
         cnt += 1
     ps._engine.check_status()

@@ -566,6 +566,15 @@ static int capture_steps(SphCtx *ctx, int nsteps, cudaGraphExec_t *out, int64_t 
     return SPH_OK;
 }
 
+int sph_get_rigid_state(SphCtx *ctx, int32_t body, float *out_dev12, void *stream) {
+    if (!ctx || !out_dev12) return SPH_E_ARG;
+    if (body < 0 || body >= (int)ctx->bodies.size()) return fail(ctx, SPH_E_ARG, "rigid body index out of range");
+    const RigidBodyDev *B = dev_bodies(ctx) + body;
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_dev12, B->R, sizeof(float) * 12, cudaMemcpyDeviceToDevice,
+                                  static_cast<cudaStream_t>(stream)));  // R[9] and cm[3] are adjacent
+    return SPH_OK;
+}
+
 int sph_step(SphCtx *ctx, int32_t nsteps, void *stream) {
     if (!ctx || nsteps < 0) return SPH_E_ARG;
     if (ctx->P.n == 0) return SPH_OK;

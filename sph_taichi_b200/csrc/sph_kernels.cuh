@@ -499,7 +499,8 @@ constexpr int RIGID_THREADS = 1024;
 struct RigidBodyDev {
     int32_t object_id, solid_begin, solid_end;
     float rest_cm[3];
-    float R[9];
+    float R[9];   // rotation of the last solve_constraints
+    float cm[3];  // centre of mass of the last solve_constraints
 };
 
 template <int NV>
@@ -607,6 +608,7 @@ __global__ void __launch_bounds__(RIGID_THREADS) k_rigid(DevParams P, DevArrays 
         for (int k = 0; k < 9; ++k) { Rf[k] = (float)Rd[k]; if (!(fabsf(Rf[k]) < 1e-6f)) all_small = false; }
         if (all_small) { for (int k = 0; k < 9; ++k) Rf[k] = (k % 4 == 0) ? 1.0f : 0.0f; }
         for (int k = 0; k < 9; ++k) { s_R[k] = Rf[k]; B->R[k] = Rf[k]; if (out) out[k] = Rf[k]; }
+        B->cm[0] = cmx; B->cm[1] = cmy; B->cm[2] = cmz;
     }
     __syncthreads();
     for (int s = b0 + threadIdx.x; s < b1; s += blockDim.x) {

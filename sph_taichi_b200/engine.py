@@ -178,6 +178,14 @@ class Engine:
                     "sph_solve_constraints")
         return out.view(3, 3)
 
+    def rigid_state(self, body_index):
+        """(R [3,3], cm [3]) of the body's last shape-matching solve, as numpy arrays."""
+        out = torch.empty(12, dtype=torch.float32, device=self.device)
+        self._check(self.lib.sph_get_rigid_state(self.ctx, int(body_index), out.data_ptr(), self._stream()),
+                    "sph_get_rigid_state")
+        h = out.cpu().numpy()
+        return h[:9].reshape(3, 3), h[9:]
+
     def set_dfsph(self, enable=True):
         self._check(self.lib.sph_set_dfsph(self.ctx, int(bool(enable))), "sph_set_dfsph")
 

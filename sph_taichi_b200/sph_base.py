@@ -87,11 +87,15 @@ class SPHBase:
                     self._update_mesh(r_obj_id, R)
                 self.enforce_boundary_3D(ps.material_solid)
 
-    def _update_mesh(self, r_obj_id, R):
-        # for OBJ export only (sph_base.py:253-257)
-        obj = self.ps.object_collection[r_obj_id]
-        cm = self.compute_com_kernel(r_obj_id)
-        ret = R.cpu().numpy() @ (obj["restPosition"] - obj["restCenterOfMass"]).T
+    def _update_mesh(self, r_obj_id, R=None):
+        """Posed mesh vertices for the OBJ export (sph_base.py:253-257): cm + R (rest - rest_cm)."""
+        ps = self.ps
+        obj = ps.object_collection[r_obj_id]
+        if R is None:  # fused step: R and cm stayed on the device
+            R, cm = ps._engine.rigid_state(ps._body_index[r_obj_id])
+        else:
+            R, cm = R.cpu().numpy(), self.compute_com_kernel(r_obj_id)
+        ret = R @ (obj["restPosition"] - obj["restCenterOfMass"]).T
         obj["meshVertices"] = cm + ret.T
 
     # ---- step (sph_base.py:263-271) ----------------------------------------------------------------
@@ -105,10 +109,9 @@ class SPHBase:
             ps._engine.step(n)
             ps._after_engine()
             if ps.cfg.get_cfg("exportObj"):
-                for oid, b in ps._body_index.items():
+                for oid in ps._body_index:
                     if "restPosition" in ps.object_collection[oid]:
-                        import torch
-                        self._update_mesh(oid, torch.eye(3))  # TODO(round 2): fetch R from the engine
+                        self._update_mesh(oid)
             return
         for _ in range(n):
             ps.initialize_particle_system()
