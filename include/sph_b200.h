@@ -166,8 +166,10 @@ int sph_dfsph_op(SphCtx *ctx, int32_t op, float arg, void *out_dev, void *stream
  * with NCCL straight out of / into the packed arrays (sph_state_offsets), appends what it
  * received behind the local records (sph_slab_set_counts) and calls sph_slab_step, which
  * classifies every record as owned / ghost / dropped from its position alone, sorts, reports
- * the next send ranges in info_dev[8] = {live, sendL_begin, sendL_end, sendR_begin, sendR_end,
- * processed, owned, status} and advances the owned particles. */
+ * the next send ranges in info_dev[12] = {live, sendL_begin, sendL_end, sendR_begin, sendR_end,
+ * processed, owned, status, sendL_end_wide, sendR_begin_wide, x_lo, x_hi} and advances the owned
+ * particles.  Calling sph_slab_configure again between steps moves the slab by at most one layer per
+ * side (load re-balancing); on such a step the neighbours exchange the *_wide ranges. */
 int sph_slab_configure(SphCtx *ctx, int32_t x_lo, int32_t x_hi, int32_t ghost_layers);
 int sph_slab_set_counts(SphCtx *ctx, int64_t n_local, int64_t n_recv);
 int sph_state_offsets(SphCtx *ctx, uint64_t *out5); /* byte offsets of posm, veld, x0id, misc, acc in the workspace */

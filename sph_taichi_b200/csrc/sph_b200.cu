@@ -637,7 +637,7 @@ int sph_slab_step(SphCtx *ctx, int32_t *info_dev, int32_t sort_only, void *strea
     if (!ctx->P.slab_on) return fail(ctx, SPH_E_ARG, "sph_slab_configure was not called");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const DevParams &P = ctx->P;
-    if (P.n == 0) { CUDA_TRY(ctx, cudaMemsetAsync(info_dev, 0, 32, st)); return SPH_OK; }
+    if (P.n == 0) { CUDA_TRY(ctx, cudaMemsetAsync(info_dev, 0, 48, st)); return SPH_OK; }
     int rc = launch_neighbor_build(ctx, st, nullptr, &ctx->launches, /*move_acc=*/false);
     if (rc) return rc;
     k_slab_info<<<1, 32, 0, st>>>(P, ctx->S, info_dev);

@@ -85,7 +85,6 @@ __global__ void k_hash_count(DevParams P, DevArrays S) {
             // the ghost band goes to the trash bucket C, which sorts to the end.
             float4 m = S.misc[i];
             uint32_t fl = __float_as_uint(m.z);
-            bool received = i >= P.n_local;
             bool in_slab = ci >= P.sx0 && ci < P.sx1;
             bool in_band = ci >= P.sx0 - P.sgw && ci < P.sx1 + P.sgw;
             bool was_ghost = (fl & FLAG_GHOST) != 0;
@@ -93,10 +92,12 @@ __global__ void k_hash_count(DevParams P, DevArrays S) {
                 c = P.C;  // last step's ghosts (local) or a neighbour's ghost (received): drop
             } else if (in_slab) {
                 // stays / becomes owned
-            } else if (received && in_band) {
+            } else if (in_band) {
+                // a neighbour's particle, or one of mine that just left the slab (the neighbour adopts
+                // it from the records I sent; I keep my copy as this step's ghost)
                 reinterpret_cast<float *>(S.misc + i)[2] = __uint_as_float(fl | FLAG_GHOST);
             } else {
-                c = P.C;  // left my slab (the neighbour adopts it) or outside the band
+                c = P.C;  // outside the band
             }
         }
         S.cid[i] = c;
@@ -133,6 +134,11 @@ __global__ void k_slab_info(DevParams P, DevArrays S, int32_t *info) {
     info[5] = P.n;                                      // records processed (live + trash)
     info[6] = info[4] - info[1];                        // owned particles
     info[7] = (int32_t)(*S.status);
+    // one layer wider, used on the steps where the slab cut between two ranks moves by a layer
+    info[8] = start_of_layer(min(P.sx0 + P.sgw + 2, P.sx1));
+    info[9] = start_of_layer(max(P.sx1 - P.sgw - 2, P.sx0));
+    info[10] = P.sx0;
+    info[11] = P.sx1;
 }
 
 // In-place inclusive prefix sum over the per-cell counts (the reference's

@@ -35,6 +35,8 @@ import torch
 import torch.distributed as dist
 
 GHOST_LAYERS = 2
+INFO_INTS = 12   # see include/sph_b200.h: sph_slab_step
+MIN_WIDTH_REBALANCE = GHOST_LAYERS + 3  # a slab must still contain its wide send range after giving a layer away
 RECORD_ARRAYS = 4  # posm, veld, x0id, misc (acc is recomputed every step and not exchanged)
 
 
@@ -80,7 +82,7 @@ class EngineBackend:
         self.m_V0 = float(np.float32(0.8 * (2 * radius) ** 3))
         self.n_max = int(n_max)
         self.eng = _engine.Engine(params, n_max=self.n_max, n_solid=0, n_bodies=0, device=self.device)
-        self.info_dev = torch.zeros(8, dtype=torch.int32, device=self.device)
+        self.info_dev = torch.zeros(INFO_INTS, dtype=torch.int32, device=self.device)
         self._floats = self.eng.workspace.view(torch.uint8)
 
     def load(self, arrays):
@@ -163,9 +165,11 @@ class EngineBackend:
 class SlabSimulation:
     """The sharded step protocol; see the module docstring."""
 
-    def __init__(self, backend, slabs, rank, world, group=None):
+    def __init__(self, backend, slabs, rank, world, group=None, rebalance_every=8):
         self.b = backend
-        self.slabs = slabs
+        self.slabs = [tuple(int(v) for v in s_) for s_ in slabs]
+        self.rebalance_every = int(rebalance_every)  # 0 disables; at most one layer per cut and event
+        self.rebalances = 0
         self.rank, self.world = rank, world
         self.group = group
         self.lo, self.hi = slabs[rank]
@@ -180,15 +184,15 @@ class SlabSimulation:
         the collective and the D2H copy run on a side stream so the pair kernels start immediately."""
         if not info_dev.is_cuda:
             if self.world == 1:
-                gathered = info_dev.clone().view(1, 8)
+                gathered = info_dev.clone().view(1, INFO_INTS)
             else:
-                gathered = torch.empty((self.world, 8), dtype=info_dev.dtype)
+                gathered = torch.empty((self.world, INFO_INTS), dtype=info_dev.dtype)
                 dist.all_gather_into_tensor(gathered.view(-1), info_dev, group=self.group)
             self._pending = (gathered, None, None)
             return
         if not hasattr(self, "_pinned"):
-            self._pinned = [torch.empty((self.world, 8), dtype=info_dev.dtype).pin_memory() for _ in range(2)]
-            self._gathered = [torch.empty((self.world, 8), dtype=info_dev.dtype, device=info_dev.device) for _ in range(2)]
+            self._pinned = [torch.empty((self.world, INFO_INTS), dtype=info_dev.dtype).pin_memory() for _ in range(2)]
+            self._gathered = [torch.empty((self.world, INFO_INTS), dtype=info_dev.dtype, device=info_dev.device) for _ in range(2)]
             self._events = [torch.cuda.Event() for _ in range(2)]
             self._side = torch.cuda.Stream(device=info_dev.device)
             self._flip = 0
@@ -227,9 +231,26 @@ class SlabSimulation:
         me = self.info_all[self.rank]
         n_live = int(me[0])
         left, right = self.rank - 1, self.rank + 1
-        n_from_left = int(self.info_all[left][4] - self.info_all[left][3]) if left >= 0 else 0
-        n_from_right = int(self.info_all[right][2] - self.info_all[right][1]) if right < self.world else 0
-        sl0, sl1, sr0, sr1 = (int(v) for v in me[1:5])
+        moves = self._plan_rebalance()  # moves[b] in {-1, 0, +1}: shift of the cut between ranks b-1 and b
+        wide_l = left >= 0 and moves[self.rank] != 0
+        wide_r = right < self.world and moves[right] != 0
+
+        def right_range(row, wide):   # what a rank sends to its RIGHT neighbour
+            return (int(row[9]) if wide else int(row[3])), int(row[4])
+
+        def left_range(row, wide):    # what a rank sends to its LEFT neighbour
+            return int(row[1]), (int(row[8]) if wide else int(row[2]))
+
+        n_from_left = 0
+        if left >= 0:
+            a_, b_ = right_range(self.info_all[left], wide_l)
+            n_from_left = b_ - a_
+        n_from_right = 0
+        if right < self.world:
+            a_, b_ = left_range(self.info_all[right], wide_r)
+            n_from_right = b_ - a_
+        sl0, sl1 = left_range(me, wide_l)
+        sr0, sr1 = right_range(me, wide_r)
         if n_live + n_from_left + n_from_right > self.b.n_max:
             raise RuntimeError(f"rank {self.rank}: slab capacity exceeded ({n_live}+{n_from_left}+{n_from_right} > "
                                f"{self.b.n_max}); raise capacity_factor")
@@ -259,6 +280,13 @@ class SlabSimulation:
         t3 = time.perf_counter()
         if gp: gp[1].record()
         self.halo_bytes += 16 * RECORD_ARRAYS * (n_from_left + n_from_right)
+        if any(moves):
+            cuts = [s_[0] for s_ in self.slabs] + [self.slabs[-1][1]]
+            cuts = [c + m for c, m in zip(cuts, moves + [0])]
+            self.slabs = [(cuts[r], cuts[r + 1]) for r in range(self.world)]
+            self.lo, self.hi = self.slabs[self.rank]
+            self.b.configure(self.lo, self.hi, GHOST_LAYERS)
+            self.rebalances += 1
         info = self.b.sort(n_live, n_from_left + n_from_right)
         t4 = time.perf_counter()
         if gp: gp[2].record()
@@ -284,6 +312,24 @@ class SlabSimulation:
                 print(f"[rank {self.rank}] " "[slab gpu us/step] exchange=%.0f sort=%.0f gather_info=%.0f compute=%.0f n_live=%d recv=%d" % (
                     *seg, n_live, n_from_left + n_from_right), flush=True)
                 self._gpu_ev.clear()
+
+    def _plan_rebalance(self):
+        """Every rank derives the same decision from the all-gathered owned counts: a cut moves one layer
+        toward the heavier side when the difference exceeds ~1.2 layers' worth of particles."""
+        moves = [0] * self.world  # moves[0] is the domain edge and never moves
+        if not self.rebalance_every or self.world == 1 or (self.steps_done % self.rebalance_every) != 0:
+            return moves
+        owned = [int(v) for v in self.info_all[:, 6]]
+        width = [hi - lo for lo, hi in self.slabs]
+        for b in range(1, self.world):
+            l_, r_ = b - 1, b
+            if owned[l_] - owned[r_] > 1.2 * owned[l_] / max(width[l_], 1) and width[l_] > MIN_WIDTH_REBALANCE:
+                moves[b] = -1   # the left rank gives its last layer to the right rank
+                width[l_] -= 1; width[r_] += 1
+            elif owned[r_] - owned[l_] > 1.2 * owned[r_] / max(width[r_], 1) and width[r_] > MIN_WIDTH_REBALANCE:
+                moves[b] = +1
+                width[l_] += 1; width[r_] -= 1
+        return moves
 
     def owned_state(self):
         self._await_info()

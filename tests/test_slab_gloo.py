@@ -66,11 +66,10 @@ class OracleSlabBackend:
         flat = (cells[:, 0] * g[1] + cells[:, 1]) * g[2] + cells[:, 2]
         flags = r[3][:n, 2].copy().view(np.uint32)
         ci = cells[:, 0]
-        received = np.arange(n) >= n_local
         in_slab = (ci >= self.lo) & (ci < self.hi)
         in_band = (ci >= self.lo - self.g) & (ci < self.hi + self.g)
         was_ghost = (flags & 4) != 0
-        new_ghost = ~was_ghost & ~in_slab & received & in_band
+        new_ghost = ~was_ghost & ~in_slab & in_band
         dead = was_ghost | (~in_slab & ~new_ghost)
         flags = np.where(new_ghost, flags | 4, flags)
         r[3][:n, 2] = flags.view(np.float32)
@@ -90,7 +89,8 @@ class OracleSlabBackend:
         live = int(cell_end[self.C - 1])
         self.live = live
         info = [live, start(self.lo), start(min(self.lo + self.g + 1, self.hi)),
-                start(max(self.hi - self.g - 1, self.lo)), start(self.hi), n, 0, 0]
+                start(max(self.hi - self.g - 1, self.lo)), start(self.hi), n, 0, 0,
+                start(min(self.lo + self.g + 2, self.hi)), start(max(self.hi - self.g - 2, self.lo)), self.lo, self.hi]
         info[6] = info[4] - info[1]
         self.launches += 5
         return torch.tensor(info, dtype=torch.int32)
@@ -126,7 +126,7 @@ class OracleSlabBackend:
         pass
 
 
-def _worker(rank, world, port, scene_dict, steps, out_dir):
+def _worker(rank, world, port, scene_dict, steps, out_dir, skew=0, rebalance_every=8):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -140,11 +140,15 @@ def _worker(rank, world, port, scene_dict, steps, out_dir):
         gx = int(np.ceil(np.array(cfg.get_cfg("domainEnd")) / h).astype(int)[0])
         hist = np.bincount(slab.layer_of(arrays["x"], h), minlength=gx)[:gx]
         slabs = slab.plan_slabs(hist, world)
+        if skew:  # deliberately unbalanced start: shift every interior cut
+            cuts = [s_[0] for s_ in slabs] + [slabs[-1][1]]
+            cuts = [cuts[0]] + [c + skew for c in cuts[1:-1]] + [cuts[-1]]
+            slabs = [(cuts[r], cuts[r + 1]) for r in range(world)]
         lo, hi = slabs[rank]
         mine, n_mine = slab.select_owned(arrays, h, lo, hi)
         backend = OracleSlabBackend(scene_dict, n_max=2 * counts["total"] + 16)
         backend.load(mine)
-        sim = slab.SlabSimulation(backend, slabs, rank, world)
+        sim = slab.SlabSimulation(backend, slabs, rank, world, rebalance_every=rebalance_every)
         sim.initialize(n_mine)
         owned_hist = []
         for _ in range(steps):
@@ -152,7 +156,7 @@ def _worker(rank, world, port, scene_dict, steps, out_dir):
             owned_hist.append(sim.owned_count())
         x, v, x0 = sim.owned_state()
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x=x, v=v, x0=x0, owned=np.array(owned_hist),
-                 slabs=np.array(slabs), halo=sim.halo_bytes)
+                 slabs=np.array(sim.slabs), slabs0=np.array(slabs), halo=sim.halo_bytes, rebalances=sim.rebalances)
     finally:
         dist.destroy_process_group()
 
@@ -200,3 +204,29 @@ def test_sharded_run_matches_single_domain_oracle(world):
     owned0 = [int(p["owned"][0]) for p in parts]; owned1 = [int(p["owned"][-1]) for p in parts]
     assert owned0 != owned1
     assert all(int(p["halo"]) > 0 for p in parts)
+
+
+def test_rebalancing_moves_cuts_and_keeps_parity():
+    """Start from deliberately skewed cuts; the balancer must move them (one layer per event) and the
+    run must still reproduce the single-domain oracle."""
+    from oracle.sph_oracle import OracleSim
+    sc = scene.dam_break_box([32, 8, 8], domain_end=[1.6, 0.5, 0.32], start=[0.06, 0.06, 0.06])
+    sc["FluidBlocks"][0]["velocity"] = [1.0, 0.0, 0.0]
+    steps, world = 30, 2
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_worker, args=(world, _free_port(), sc, steps, td, -3, 2), nprocs=world, join=True)
+        parts = [np.load(os.path.join(td, f"rank{r}.npz")) for r in range(world)]
+    assert int(parts[0]["rebalances"]) >= 2
+    assert not np.array_equal(parts[0]["slabs"], parts[0]["slabs0"])
+    own = [int(p["owned"][-1]) for p in parts]
+    own0 = [int(p["owned"][0]) for p in parts]
+    assert abs(own[0] - own[1]) < abs(own0[0] - own0[1])     # better balanced than at the start
+    x = np.concatenate([p["x"] for p in parts]); x0 = np.concatenate([p["x0"] for p in parts])
+    o = OracleSim(sc, threads=2)
+    o.initialize()
+    for _ in range(steps):
+        o.step()
+    assert x.shape[0] == o.n
+    ks, ko = np.lexsort((x0[:, 2], x0[:, 1], x0[:, 0])), np.lexsort((o.x_0[:, 2], o.x_0[:, 1], o.x_0[:, 0]))
+    assert np.array_equal(x0[ks], o.x_0[ko])
+    assert np.abs(x[ks] - o.x[ko]).max() / 0.02 < 1e-3
