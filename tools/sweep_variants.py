@@ -6,8 +6,8 @@ from sph_taichi_b200 import ParticleSystem, SimConfig, scene
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--scene", default="dragon_bath")
-ap.add_argument("--dv", type=int, nargs="*", default=[0, 1, 2, 3, 4, 5])
-ap.add_argument("--fv", type=int, nargs="*", default=[0, 1, 2, 3, 4, 5])
+ap.add_argument("--dv", type=int, nargs="*", default=[0, 1])
+ap.add_argument("--fv", type=int, nargs="*", default=[0, 1])
 ap.add_argument("--pairs", type=str, default="", help="explicit dv:fv pairs, comma separated")
 ap.add_argument("--warm", type=int, default=100)
 a = ap.parse_args()
