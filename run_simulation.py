@@ -24,12 +24,19 @@ def write_ply_ascii(path, pos):
 
 if __name__ == "__main__":
     parser = argparse.ArgumentParser(description="SPH (B200 engine)")
-    parser.add_argument("--scene_file", default="", help="scene file")
+    parser.add_argument("--scene_file", default="", help="scene file (JSON, the reference's schema)")
+    parser.add_argument("--scene", default="", help="built-in scene name instead of a file, e.g. dragon_bath "
+                                                    "(python -m sph_taichi_b200.scene DIR writes them as JSON)")
     parser.add_argument("--frames", type=int, default=100, help="render updates to run (the reference loops until the window closes)")
     parser.add_argument("--quiet", action="store_true")
     args = parser.parse_args()
-    scene_path = args.scene_file
-    config = SimConfig(scene_file_path=scene_path)
+    if args.scene:
+        from sph_taichi_b200 import scene as _scene
+        scene_path = args.scene + ".json"
+        config = SimConfig(_scene.NAMED_SCENES[args.scene]())
+    else:
+        scene_path = args.scene_file
+        config = SimConfig(scene_file_path=scene_path)
     scene_name = scene_path.split("/")[-1].split(".")[0]
 
     substeps = config.get_cfg("numberOfStepsPerRenderUpdate")

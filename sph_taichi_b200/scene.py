@@ -182,7 +182,9 @@ NAMED_SCENES = {
 
 
 def write_scene_files(out_dir=None):
-    """(Re)generate ``data/scenes/*.json`` from the builders above."""
+    """Materialise the named scenes as JSON files (``python -m sph_taichi_b200.scene [out_dir]``).
+
+    The files are generated, not committed: they necessarily carry the reference's parameter values."""
     out_dir = out_dir or os.path.join(_PKG_DIR, "data", "scenes")
     os.makedirs(out_dir, exist_ok=True)
     for name, fn in NAMED_SCENES.items():
@@ -306,3 +308,9 @@ def assemble_particles(cfg, dim, diameter, verbose=False):
         arrays = {k: np.zeros((0, 3) if k in ("x", "v", "color") else (0,), np.float32) for k in keys}
     counts = dict(fluid=n_fluid, solid=n_rigid, total=n_fluid + n_rigid)
     return arrays, object_collection, rigid_ids, counts
+
+
+if __name__ == "__main__":
+    import sys
+    write_scene_files(sys.argv[1] if len(sys.argv) > 1 else None)
+    print("wrote", ", ".join(sorted(NAMED_SCENES)))

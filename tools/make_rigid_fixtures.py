@@ -8,7 +8,7 @@ copied into this repo):
 For every ``RigidBodies`` entry of the bath scenes it runs ``voxelizer.py`` on the
 reference mesh with the scene's transform and stores the filled lattice indices
 (int16) plus the pitch in ``sph_taichi_b200/data/rigid/<scene>_<objectId>.npz``.
-Points are ``lattice * pitch``.  It also rewrites ``data/scenes/*.json``.
+Points are ``lattice * pitch``.
 """
 import os
 import sys
@@ -35,7 +35,6 @@ def main():
             np.savez_compressed(dst, lattice=idx.astype(np.int16), pitch=np.float64(pitch),
                                 rest_center_of_mass=verts.mean(axis=0))
             print(f"{name} body {body['objectId']}: {idx.shape[0]} voxels -> {dst}")
-    scene.write_scene_files()
 
 
 if __name__ == "__main__":
