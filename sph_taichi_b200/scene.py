@@ -227,7 +227,8 @@ def rigid_body_lattice(body, diameter, scene_dir):
             return idx, verts, faces
     fix = body.get("voxelizedPointsFile")
     if fix:
-        for path in (fix, os.path.join(scene_dir, fix), os.path.join(_PKG_DIR, "data", "scenes", fix)):
+        for path in (fix, os.path.join(scene_dir, fix), os.path.join(_PKG_DIR, "data", "rigid", os.path.basename(fix))):
+            path = os.path.normpath(path)
             if os.path.isfile(path):
                 with np.load(path) as z:
                     if abs(float(z["pitch"]) - diameter) > 1e-12:
