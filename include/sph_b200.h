@@ -175,6 +175,9 @@ int sph_slab_set_counts(SphCtx *ctx, int64_t n_local, int64_t n_recv);
 int sph_state_offsets(SphCtx *ctx, uint64_t *out5); /* byte offsets of posm, veld, x0id, misc, acc in the workspace */
 int sph_slab_step(SphCtx *ctx, int32_t *info_dev, int32_t sort_only, void *stream);
 int sph_slab_compute(SphCtx *ctx, void *stream); /* the part of sph_slab_step after the sort */
+/* the same in two launches: phase 0 = density + the particles of this rank's send ranges, phase 1 = the
+ * rest; the caller posts the next halo exchange in between so that it overlaps the interior work */
+int sph_slab_compute_split(SphCtx *ctx, const int32_t *info_dev, int32_t phase, void *stream);
 /* CUDA-event timing of the density and force launches of sph_slab_compute: enable != 0 switches it on;
  * ms_out (may be NULL) receives {density_ms, force_ms} of the last timed call (synchronises). */
 int sph_slab_pair_times(SphCtx *ctx, int32_t enable, float *ms_out);

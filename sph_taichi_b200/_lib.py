@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "sph_advect", "sph_enforce_boundary", "sph_set_rigid_bodies", "sph_compute_com", "sph_compute_rigid_rest_cm",
     "sph_solve_constraints", "sph_get_rigid_state", "sph_step", "sph_read_status", "sph_clear_status", "sph_particle_count",
     "sph_launch_count", "sph_profile_step", "sph_timer_name", "sph_slab_configure", "sph_slab_set_counts",
-    "sph_state_offsets", "sph_slab_step", "sph_slab_compute", "sph_slab_pair_times", "sph_set_dfsph", "sph_dfsph_op",
+    "sph_state_offsets", "sph_slab_step", "sph_slab_compute", "sph_slab_compute_split", "sph_slab_pair_times", "sph_set_dfsph", "sph_dfsph_op",
 ]
 
 
@@ -125,6 +125,7 @@ def load():
         "sph_state_offsets": (C.c_int, [vp, C.POINTER(u64)]),
         "sph_slab_step": (C.c_int, [vp, vp, i32, vp]),
         "sph_slab_compute": (C.c_int, [vp, vp]),
+        "sph_slab_compute_split": (C.c_int, [vp, vp, i32, vp]),
         "sph_set_dfsph": (C.c_int, [vp, i32]),
         "sph_dfsph_op": (C.c_int, [vp, i32, C.c_float, vp, vp]),
         "sph_slab_pair_times": (C.c_int, [vp, i32, C.POINTER(C.c_float)]),

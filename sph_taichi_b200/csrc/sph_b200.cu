@@ -234,10 +234,12 @@ void launch_pair_density(SphCtx *c, cudaStream_t st, int64_t *kernels) {
     else k_density_tma<true><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
     *kernels += 1;
 }
-void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels) {
+void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels,
+                                  const int32_t *split_info = nullptr, int split_mode = 0) {
     const DevParams &P = c->P;
     if (P.uniform_fluid && c->var_force != 0) {
-        k_force_packed<4, 128, true><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
+        k_force_packed<FORCE_BATCH, FORCE_THREADS, true><<<blocks_for(P.n, FORCE_THREADS), FORCE_THREADS, 0, st>>>(
+            P, c->S, split_info, split_mode);
         *kernels += 1;
         if (tm) tm->mark(T_ADVECT);
         if (c->has_dynamic_solids && P.n_solid > 0) {
@@ -246,7 +248,7 @@ void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, in
         }
         return;
     }
-    if (P.uniform_fluid) k_force_packed<4, 128, false><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
+    if (P.uniform_fluid) k_force_packed<4, 128, false><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S, nullptr, 0);
     else k_force_general<4, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
     if (tm) tm->mark(T_ADVECT);
     k_advect<true><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
@@ -668,6 +670,29 @@ int sph_slab_compute(SphCtx *ctx, void *stream) {
         launch_pair_force_and_advect(ctx, st, nullptr, &ctx->launches);
     }
     ctx->built = false; ctx->list_valid = false;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
+// sph_slab_compute in two phases so that the caller can start the next halo exchange in between:
+// phase 0 = density pass + forces/integration of the particles inside this rank's (wide) send ranges,
+// phase 1 = forces/integration of all other owned particles.  info_dev is the array sph_slab_step wrote.
+int sph_slab_compute_split(SphCtx *ctx, const int32_t *info_dev, int32_t phase, void *stream) {
+    if (!ctx || !info_dev || (phase != 0 && phase != 1)) return SPH_E_ARG;
+    if (!ctx->P.slab_on) return fail(ctx, SPH_E_ARG, "sph_slab_configure was not called");
+    const DevParams &P = ctx->P;
+    if (P.n == 0) return SPH_OK;
+    if (!(P.uniform_fluid && ctx->var_force != 0))
+        return fail(ctx, SPH_E_ARG, "split compute needs the uniform-fluid force kernel; use sph_slab_compute");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (phase == 0) {
+        if (!ctx->built) return fail(ctx, SPH_E_ARG, "sph_slab_compute_split needs a fresh sph_slab_step(sort_only = 1)");
+        launch_pair_density(ctx, st, &ctx->launches);
+        launch_pair_force_and_advect(ctx, st, nullptr, &ctx->launches, info_dev, 0);
+    } else {
+        launch_pair_force_and_advect(ctx, st, nullptr, &ctx->launches, info_dev, 1);
+        ctx->built = false; ctx->list_valid = false;
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     return SPH_OK;
 }

@@ -994,10 +994,28 @@ __device__ __forceinline__ void force_pair_packed(const DevParams &P, const DevA
 // fpos / fvel.  Because nothing reads posm / veld of OTHER particles here, FUSE_ADVECT lets the
 // epilogue integrate the particle and clamp it to the walls in place (advect + enforce_boundary_3D
 // (fluid), WCSPH.py:143-149, sph_base.py:149-179) -- one launch and one pass over the state less.
+#ifndef FORCE_MIN_BLOCKS
+#define FORCE_MIN_BLOCKS 8  // 64 registers: measured best of B in {2,3,4,6} x min-blocks {1,8,10}
+#endif
+#ifndef FORCE_BATCH
+#define FORCE_BATCH 4
+#endif
+#ifndef FORCE_THREADS
+#define FORCE_THREADS 128
+#endif
+// split_info / split_mode (slab mode): process only the particles inside (mode 0) or outside (mode 1)
+// the index ranges this rank sends to its neighbours (info[1..8) / info[9..4), see k_slab_info), so
+// that the halo exchange of the next step can start while the interior is still being computed.
 template <int B, int THREADS, bool FUSE_ADVECT>
-__global__ void __launch_bounds__(THREADS) k_force_packed(DevParams P, DevArrays S) {
+__global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevParams P, DevArrays S,
+                                                                            const int32_t *__restrict__ split_info,
+                                                                            int split_mode) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
+    if (split_info) {
+        bool boundary = (i >= split_info[1] && i < split_info[8]) || (i >= split_info[9] && i < split_info[4]);
+        if ((split_mode == 0) != boundary) return;
+    }
     if (P.slab_on && S.grid_ids[i] >= P.C) return;
     float4 mi = S.misc[i];
     uint32_t fl = __float_as_uint(mi.z);

@@ -139,6 +139,12 @@ class EngineBackend:
         e = self.eng
         e._check(e.lib.sph_slab_compute(e.ctx, e._stream()), "sph_slab_compute")
 
+    def compute_phase(self, phase):
+        """phase 0: density + forces of the send ranges; phase 1: forces of the interior."""
+        e = self.eng
+        e._check(e.lib.sph_slab_compute_split(e.ctx, self.info_dev.data_ptr(), int(phase), e._stream()),
+                 "sph_slab_compute_split")
+
     def owned_state(self, info_row):
         """(x, v, x_0) of the owned particles as numpy arrays."""
         v = self.record_views()
@@ -169,6 +175,8 @@ class SlabSimulation:
         self.b = backend
         self.slabs = [tuple(int(v) for v in s_) for s_ in slabs]
         self.rebalance_every = int(rebalance_every)  # 0 disables; at most one layer per cut and event
+        self.overlap = True   # post the next exchange while the interior particles are still computed
+        self._exch = None
         self.rebalances = 0
         self.rank, self.world = rank, world
         self.group = group
@@ -223,11 +231,12 @@ class SlabSimulation:
         info = self.b.sort(n_initial, 0)
         self._gather_info(info)
 
-    def step(self):
-        prof = self.__dict__.setdefault("_prof", [0.0] * 6) if os.environ.get("SPH_SLAB_PROF") else None
-        t0 = time.perf_counter()
-        self._await_info()
-        t1 = time.perf_counter()
+    # -- one sharded step ----------------------------------------------------------------------
+    def _post_exchange(self, after_event=None):
+        """Decide re-balancing, derive the send / receive ranges from the freshly gathered info rows and
+        post ONE batched NCCL send/recv group.  On CUDA the group is issued on a communication stream that
+        waits only for ``after_event`` (the boundary particles are final), so it overlaps whatever the
+        main stream does next.  Returns the pending-exchange record consumed by ``step``."""
         me = self.info_all[self.rank]
         n_live = int(me[0])
         left, right = self.rank - 1, self.rank + 1
@@ -269,49 +278,71 @@ class SlabSimulation:
                     ops.append(dist.P2POp(dist.isend, arr[sr0:sr1], right, self.group))
                 if n_from_right:
                     ops.append(dist.P2POp(dist.irecv, arr[a1:a1 + n_from_right], right, self.group))
-        t2 = time.perf_counter()
-        gp = None
-        if prof is not None:
-            gp = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-            gp[0].record()
+        reqs, comm = [], None
         if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        t3 = time.perf_counter()
-        if gp: gp[1].record()
+            if views[0].is_cuda:
+                if not hasattr(self, "_comm"):
+                    self._comm = torch.cuda.Stream(device=views[0].device)
+                comm = self._comm
+                main = torch.cuda.current_stream(views[0].device)
+                if after_event is not None:
+                    comm.wait_event(after_event)
+                else:
+                    comm.wait_stream(main)
+                with torch.cuda.stream(comm):
+                    reqs = dist.batch_isend_irecv(ops)
+                    for req in reqs:
+                        req.wait()  # the comm stream (not the host, not the main stream) waits for NCCL
+            else:
+                reqs = dist.batch_isend_irecv(ops)
         self.halo_bytes += 16 * RECORD_ARRAYS * (n_from_left + n_from_right)
-        if any(moves):
+        return {"n_live": n_live, "n_recv": n_from_left + n_from_right, "moves": moves, "reqs": reqs, "comm": comm}
+
+    def step(self):
+        if self._exch is None:  # nothing pre-posted: first step, or overlap switched off
+            self._await_info()
+            self._exch = self._post_exchange(None)
+        ex, self._exch = self._exch, None
+        if ex["comm"] is not None:
+            torch.cuda.current_stream().wait_stream(ex["comm"])  # received records are in place
+        else:
+            for req in ex["reqs"]:
+                req.wait()
+        if any(ex["moves"]):
             cuts = [s_[0] for s_ in self.slabs] + [self.slabs[-1][1]]
-            cuts = [c + m for c, m in zip(cuts, moves + [0])]
+            cuts = [c + m for c, m in zip(cuts, ex["moves"] + [0])]
             self.slabs = [(cuts[r], cuts[r + 1]) for r in range(self.world)]
             self.lo, self.hi = self.slabs[self.rank]
             self.b.configure(self.lo, self.hi, GHOST_LAYERS)
             self.rebalances += 1
-        info = self.b.sort(n_live, n_from_left + n_from_right)
-        t4 = time.perf_counter()
-        if gp: gp[2].record()
+        info = self.b.sort(ex["n_live"], ex["n_recv"])
         self._gather_info(info)
-        t5 = time.perf_counter()
-        if gp: gp[3].record()
-        self.b.compute()
-        if gp:
-            gp[4].record()
-            self.__dict__.setdefault("_gpu_ev", []).append(gp)
         self.steps_done += 1
-        if prof is not None:
-            t6 = time.perf_counter()
-            for k, dt in enumerate((t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t6 - t5)):
-                prof[k] += dt
-            if self.steps_done % 50 == 0:
-                names = ("await_info", "build_ops", "nccl_p2p", "sort_launch", "gather_info", "compute_launch")
-                print("[slab host us/step] " + " ".join(f"{n}={v / self.steps_done * 1e6:.0f}" for n, v in zip(names, prof)),
-                      flush=True)
-                torch.cuda.synchronize()
-                evs = self._gpu_ev[-40:]
-                seg = [sum(e[k].elapsed_time(e[k + 1]) for e in evs) / len(evs) * 1e3 for k in range(4)]
-                print(f"[rank {self.rank}] " "[slab gpu us/step] exchange=%.0f sort=%.0f gather_info=%.0f compute=%.0f n_live=%d recv=%d" % (
-                    *seg, n_live, n_from_left + n_from_right), flush=True)
-                self._gpu_ev.clear()
+        if self.overlap and self.world > 1 and hasattr(self.b, "compute_phase"):
+            # density + the particles I am about to send, then the exchange of the NEXT step goes out on
+            # the communication stream while the interior particles are still being processed
+            prof = os.environ.get("SPH_SLAB_PROF")
+            self.b.compute_phase(0)
+            ev = torch.cuda.Event(enable_timing=bool(prof))
+            ev.record()
+            self.b.compute_phase(1)  # queued first: the host-side cost of posting NCCL must not idle the GPU
+            self._await_info()       # host waits for this step's sort only; the device is busy
+            self._exch = self._post_exchange(ev)
+            if prof and self._exch["comm"] is not None:
+                e_comm = torch.cuda.Event(enable_timing=True)
+                e_comm.record(self._exch["comm"])
+                e_p1 = torch.cuda.Event(enable_timing=True)
+                e_p1.record()
+                self.__dict__.setdefault("_ovl", []).append((ev, e_comm, e_p1))
+                if self.steps_done % 50 == 0:
+                    torch.cuda.synchronize()
+                    rows = self._ovl[-40:]
+                    print(f"[rank {self.rank}] after phase 0: exchange done at +%.0f us, interior force done at +%.0f us" % (
+                        sum(a.elapsed_time(b) for a, b, _ in rows) / len(rows) * 1e3,
+                        sum(a.elapsed_time(c) for a, _, c in rows) / len(rows) * 1e3), flush=True)
+                    self._ovl.clear()
+        else:
+            self.b.compute()
 
     def _plan_rebalance(self):
         """Every rank derives the same decision from the all-gathered owned counts: a cut moves one layer
@@ -390,6 +421,8 @@ def bench_main(args):
     os.environ.setdefault("MASTER_PORT", "29511")
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
+    # the halo exchange must get SMs while the interior force pass is running
+    os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     name, sc = _bench.scene_for(world, args.scene)
     sim, n_total = build_sharded(sc, rank, world, dev)
@@ -423,6 +456,7 @@ def bench_main(args):
     clocks = sampler.stop() if sampler else None
 
     # ---- force-kernel roofline on every rank (CUDA events around the launch, 10 extra steps) ----
+    sim.overlap = False  # the per-kernel timer brackets the un-split launches
     sim.b.pair_times(True)
     fsum = dsum = 0.0
     for _ in range(10):
@@ -482,7 +516,8 @@ def bench_main(args):
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "particles": n_total, "solver": "WCSPH", "dt": sc["Configuration"]["timeStepSize"],
-                       "parallelism": f"x-slab x{world}, 2 ghost layers, 1 NCCL send/recv group per step",
+                       "parallelism": f"x-slab x{world}, 2 ghost layers, 1 NCCL send/recv group per step, overlapped with the "
+                                      "interior force pass; cuts re-balanced every 8 steps",
                        "slabs": [list(map(int, s)) for s in sim.slabs], "owned_total": int(tot[0].item()),
                        "owned_max_per_rank": int(mx[0].item()),
                        "l2": "per-rank working set (> 126 MB of packed state + neighbour lists) exceeds L2; no flush"},
