@@ -74,7 +74,6 @@ struct SphCtx {
     int body_cap = 0;
     char *ws = nullptr;
     std::vector<SphRigidBody> bodies;
-    int n_dynamic_bodies = 0;
     bool has_dynamic_solids = true;  // conservative until pack() inspects the flags
     std::string err;
     int64_t launches = 0;
@@ -579,6 +578,7 @@ int sph_get_rigid_state(SphCtx *ctx, int32_t body, float *out_dev12, void *strea
 
 int sph_step(SphCtx *ctx, int32_t nsteps, void *stream) {
     if (!ctx || nsteps < 0) return SPH_E_ARG;
+    if (ctx->P.dfsph) return fail(ctx, SPH_E_ARG, "sph_step is the fused WCSPH step; DFSPH is driven through sph_dfsph_op");
     if (ctx->P.n == 0) return SPH_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int s = 0;

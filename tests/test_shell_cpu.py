@@ -1,0 +1,160 @@
+"""Host logic of the reference-surface shells on CPU: a recording stand-in replaces the CUDA engine
+(only here, in the test) so that call sequences, field coherence and argument checks of
+ParticleSystem / SPHBase / WCSPHSolver / DFSPHSolver can be verified without a GPU."""
+import numpy as np
+import pytest
+import torch
+
+from sph_taichi_b200 import SimConfig, scene
+from tests.helpers import mixed_scene
+
+
+class RecordingEngine:
+    calls = None
+
+    def __init__(self, params, n_max, n_solid=0, n_bodies=0, device=None):
+        self.params, self.n_max = params, n_max
+        self.log = []
+        RecordingEngine.last = self
+        self._err = 1.0e9
+
+    def __getattr__(self, name):
+        def f(*a, **k):
+            self.log.append(name)
+            if name == "compute_com":
+                return torch.zeros(3)
+            if name == "solve_constraints":
+                return torch.eye(3)
+            if name in ("check_status", "read_status", "launch_count"):
+                return 0
+            return None
+        return f
+
+    def dfsph_op(self, op, arg=0.0, out=None):
+        self.log.append(f"dfsph:{op}")
+        if op == 4 and out is not None:   # density error: converge after three sweeps
+            self._err = self._err / 1.0e6
+            out.fill_(self._err)
+
+
+@pytest.fixture
+def fake_engine(monkeypatch):
+    from sph_taichi_b200 import engine
+    monkeypatch.setattr(engine, "Engine", RecordingEngine)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    yield
+
+
+def _ps(sc):
+    from sph_taichi_b200.particle_system import ParticleSystem
+    return ParticleSystem(SimConfig(sc), device="cpu")
+
+
+def test_surface_attributes_and_counts(fake_engine):
+    ps = _ps(mixed_scene())
+    for name in ("cfg", "GGUI", "dim", "domain_start", "domain_size", "particle_radius", "particle_diameter",
+                 "support_radius", "m_V0", "grid_size", "grid_num", "padding", "material_solid", "material_fluid",
+                 "simulation_method", "particle_num", "particle_max_num", "fluid_particle_num", "solid_particle_num",
+                 "num_rigid_bodies", "object_collection", "object_id_rigid_body", "object_id", "x", "x_0", "v",
+                 "acceleration", "m_V", "m", "density", "pressure", "material", "color", "is_dynamic", "grid_ids",
+                 "grid_particles_num"):
+        assert hasattr(ps, name), name
+    assert ps.material_solid == 0 and ps.material_fluid == 1
+    assert ps.particle_num[None] == ps.particle_max_num == ps.fluid_particle_num + ps.solid_particle_num
+    assert ps.support_radius == pytest.approx(0.04) and ps.m_V0 == pytest.approx(0.8 * 0.02 ** 3)
+    x = ps.x.to_numpy()
+    assert x.dtype == np.float32 and np.array_equal(x, ps.x_0.to_numpy())
+    assert np.allclose(ps.m.to_numpy(), np.float32(ps.m_V0) * ps.density.to_numpy())
+    assert ps.x[0].shape == (3,) and ps.x.shape == (ps.particle_max_num,)
+
+
+def test_step_sequences(fake_engine):
+    from sph_taichi_b200.WCSPH import WCSPHSolver
+    ps = _ps(mixed_scene())
+    s = ps.build_solver()
+    assert isinstance(s, WCSPHSolver) and s.dt[None] == pytest.approx(4e-4)
+    s.initialize()
+    eng = RecordingEngine.last
+    assert eng.log[:2] == ["set_params", "set_rigid_bodies"] or "pack" in eng.log
+    assert eng.log[-3:] == ["neighbor_build", "boundary_volume", "boundary_volume"]
+    eng.log.clear()
+    s.step()                                   # stock substep -> one fused engine call
+    assert eng.log == ["step"]
+
+    class Custom(WCSPHSolver):
+        def substep(self):
+            super().substep()
+
+    c = Custom(ps)
+    eng.log.clear()
+    c.step()                                   # overridden substep -> the reference's generic sequence
+    assert eng.log == ["neighbor_build", "boundary_volume", "compute_densities", "compute_non_pressure_forces",
+                       "compute_pressure_forces", "advect", "enforce_boundary"]
+    eng.log.clear()
+    c.dt[None] = 1e-4                          # solver.dt[None] = ... re-bakes the parameters
+    assert eng.log == ["set_params"] and ps._dt == pytest.approx(1e-4)
+
+
+def test_field_coherence_protocol(fake_engine):
+    ps = _ps(mixed_scene())
+    s = ps.build_solver()
+    s.initialize()
+    eng = RecordingEngine.last
+    eng.log.clear()
+    ps.x.to_numpy()                            # engine ahead -> unpack once, then cached
+    ps.v.to_numpy()
+    assert eng.log == ["unpack"]
+    eng.log.clear()
+    x = ps.x.to_numpy()
+    ps.x.from_numpy(x)                         # user write -> re-pack before the next engine call
+    s.step()
+    assert eng.log[-2:] == ["pack", "step"] and "set_rigid_bodies" in eng.log
+    with pytest.raises(ValueError):
+        ps.grid_ids.fill(0)                    # derived fields are read-only
+    with pytest.raises(ValueError):
+        ps.x.from_numpy(x[:-1])
+
+
+def test_argument_checks(fake_engine):
+    sc = mixed_scene()
+    sc["Configuration"]["domainStart"] = [0.1, 0.0, 0.0]
+    with pytest.raises(ValueError, match="domainStart"):
+        _ps(sc)
+    sc = mixed_scene()
+    sc["Configuration"]["simulationMethod"] = 2
+    with pytest.raises(NotImplementedError):
+        _ps(sc).build_solver()
+    ps = _ps(mixed_scene())
+    n = ps.particle_max_num
+    with pytest.raises(ValueError, match="exceeds"):
+        ps.add_particles(0, 1, np.zeros((1, 3)), np.zeros((1, 3)), np.ones(1), np.zeros(1), np.ones(1), np.ones(1),
+                         np.zeros((1, 3)))
+    assert ps.particle_num[None] == n
+    assert ps.compute_cube_particle_num([0.1, 0.1, 0.5], [1.2, 2.9, 1.6]) == 423500
+
+
+def test_dfsph_host_loops(fake_engine):
+    from sph_taichi_b200.DFSPH import DFSPHSolver
+    sc = mixed_scene()
+    sc["Configuration"]["simulationMethod"] = 4
+    sc["Configuration"]["timeStepSize"] = 0.004
+    ps = _ps(sc)
+    s = ps.build_solver()
+    assert isinstance(s, DFSPHSolver) and hasattr(ps, "dfsph_factor") and hasattr(ps, "density_adv")
+    s.initialize()
+    eng = RecordingEngine.last
+    eng.log.clear()
+    eng._err = 1.0e9
+    s.divergence_solve()
+    # compute_density_change, scale by 1/dt, then (iteration, density_change, error) until converged, scale back
+    assert eng.log[:2] == ["dfsph:2", "dfsph:5"] and eng.log[-1] == "dfsph:5"
+    sweeps = eng.log[2:-1]
+    assert sweeps[:3] == ["dfsph:6", "dfsph:2", "dfsph:4"] and len(sweeps) % 3 == 0
+    assert s.last_iterations_v == len(sweeps) // 3 - 1
+    eng.log.clear()
+    eng._err = 1.0e9
+    s.substep()
+    ops = [c for c in eng.log if c.startswith("dfsph")]
+    assert ops[0] == "dfsph:0" and ops[1] == "dfsph:1" and ops[-1] == "dfsph:10"
+    assert "dfsph:8" in ops and "dfsph:9" in ops and "dfsph:7" in ops and "dfsph:3" in ops
+    assert not s._fused_step_ok()
