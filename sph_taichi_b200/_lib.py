@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "sph_pack", "sph_unpack", "sph_unpack_xv", "sph_upload_xv", "sph_copy_grid_particles_num", "sph_neighbor_build",
     "sph_boundary_volume", "sph_compute_densities", "sph_compute_non_pressure_forces", "sph_compute_pressure_forces",
     "sph_advect", "sph_enforce_boundary", "sph_set_rigid_bodies", "sph_compute_com", "sph_compute_rigid_rest_cm",
-    "sph_solve_constraints", "sph_get_rigid_state", "sph_step", "sph_read_status", "sph_clear_status", "sph_particle_count",
+    "sph_solve_constraints", "sph_get_rigid_state", "sph_step", "sph_read_status", "sph_clear_status", "sph_neighbor_stats", "sph_particle_count",
     "sph_launch_count", "sph_profile_step", "sph_timer_name", "sph_slab_configure", "sph_slab_set_counts",
     "sph_state_offsets", "sph_slab_step", "sph_slab_compute", "sph_slab_compute_split", "sph_slab_pair_times", "sph_set_dfsph", "sph_dfsph_op",
 ]
@@ -116,6 +116,7 @@ def load():
         "sph_step": (C.c_int, [vp, i32, vp]),
         "sph_read_status": (C.c_int, [vp, C.POINTER(C.c_uint32), vp]),
         "sph_clear_status": (C.c_int, [vp, vp]),
+        "sph_neighbor_stats": (C.c_int, [vp, vp, vp]),
         "sph_particle_count": (i64, [vp]),
         "sph_launch_count": (i64, [vp]),
         "sph_profile_step": (C.c_int, [vp, C.POINTER(C.c_float), i32, vp]),

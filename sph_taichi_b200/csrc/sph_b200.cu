@@ -773,6 +773,17 @@ int sph_clear_status(SphCtx *ctx, void *stream) {
     return SPH_OK;
 }
 
+int sph_neighbor_stats(SphCtx *ctx, int32_t *out_dev4, void *stream) {
+    if (!ctx || !out_dev4) return SPH_E_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(ctx, cudaMemsetAsync(out_dev4, 0, 16, st));
+    if (ctx->P.n == 0) return SPH_OK;
+    k_neighbor_stats<<<blocks_for(ctx->P.n, 256), 256, 0, st>>>(ctx->P, ctx->S, out_dev4);
+    ctx->launches += 1;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
 int64_t sph_particle_count(const SphCtx *ctx) { return ctx ? ctx->P.n : 0; }
 int64_t sph_launch_count(const SphCtx *ctx) { return ctx ? ctx->launches : 0; }
 

@@ -69,7 +69,7 @@ struct DevArrays {
     int32_t npad;
 };
 
-constexpr int NBR_CAP = 64;
+constexpr int NBR_CAP = 96;  // soak runs of the shipped scenes peak at 54 neighbours (tools/soak.py)
 constexpr int NBR_OVERFLOW = 0x7fffffff;
 
 // |r|^2 in the reference's (and the oracle's) rounding sequence: three products, two sums, no FMA

@@ -1081,3 +1081,18 @@ __global__ void k_advect_solids(DevParams P, DevArrays S) {
     S.posm[i] = p;
     S.veld[i] = v;
 }
+
+// Diagnostics: neighbour-list statistics of the last density pass -> out[4] = {max count, particles in
+// overflow (full-scan fallback), total pairs, particles with a list}.  out must be zeroed by the caller.
+__global__ void k_neighbor_stats(DevParams P, DevArrays S, int32_t *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    if (P.slab_on && S.grid_ids[i] >= P.C) return;
+    uint32_t fl = __float_as_uint(S.misc[i].z);
+    if (!(fl & FLAG_FLUID)) return;
+    int c = S.nbr_cnt[i];
+    if (c == NBR_OVERFLOW) { atomicAdd(out + 1, 1); c = NBR_CAP; }
+    atomicMax(out + 0, c);
+    atomicAdd(out + 2, c);
+    atomicAdd(out + 3, 1);
+}

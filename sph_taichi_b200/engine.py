@@ -211,6 +211,13 @@ class Engine:
                                "out of bounds here")
         return st
 
+    def neighbor_stats(self):
+        """{max, overflow, pairs, fluid} of the neighbour lists built by the last density pass."""
+        out = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._check(self.lib.sph_neighbor_stats(self.ctx, out.data_ptr(), self._stream()), "sph_neighbor_stats")
+        m, o, p, f = (int(v) for v in out.cpu().tolist())
+        return {"max": m, "overflow": o, "pairs": p, "fluid": f, "mean": p / max(f, 1)}
+
     def launch_count(self):
         return int(self.lib.sph_launch_count(self.ctx))
 

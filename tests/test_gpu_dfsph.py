@@ -79,6 +79,23 @@ def test_dfsph_per_kernel_parity():
         s.compute_DFSPH_factor()
 
 
+def test_dfsph_kernels_on_overfull_neighbour_lists():
+    """Same kernels on a state with > 96 neighbours per particle: the 27-cell fallback of the list walk."""
+    o, ps, s = _pair(_dfsph(mixed_scene(with_dynamic=False)), seed=3, squeeze=0.6)
+    o.initialize(); s.initialize()
+    fl = o.material == 1
+    o.compute_densities(); s.compute_densities()
+    assert ps._engine.neighbor_stats()["overflow"] > 100
+    assert _maxrel(ps.density.to_numpy(), o.density) < REL
+    o.compute_DFSPH_factor(); s.compute_DFSPH_factor()
+    assert _maxrel(ps.dfsph_factor.to_numpy()[fl], o.dfsph_factor[fl]) < REL
+    o.compute_density_change(); s.compute_density_change()
+    assert _maxrel(ps.density_adv.to_numpy()[fl], o.density_adv[fl]) < 5 * REL
+    o.multiply_time_step_factor(250.0); s.multiply_time_step(ps.dfsph_factor, 250.0)
+    o.divergence_solver_iteration_kernel(); s.divergence_solver_iteration_kernel()
+    assert _maxrel(ps.v.to_numpy(), o.v) < 5 * REL
+
+
 def test_dfsph_steps_vs_oracle():
     from sph_taichi_b200 import scene
     sc = _dfsph(scene.dam_break_box([16, 20, 16], domain_end=[0.8, 0.8, 0.6], start=[0.06, 0.06, 0.06]))

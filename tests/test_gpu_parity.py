@@ -254,10 +254,13 @@ def test_out_of_grid_is_reported():
 
 
 def test_fused_step_fields_vs_oracle_and_overflow_path():
-    """Fused v2 kernels (neighbour lists) per-field parity after ONE step, on a state squeezed so
-    hard that most particles exceed NBR_CAP = 64 neighbours (exercises the full-scan fallback)."""
-    for squeeze, min_nbrs in ((1.0, 0), (0.7, 64)):
-        o, ps, solver = _pair(mixed_scene(with_dynamic=False), seed=11, amp=0.002)
+    """Fused production kernels (neighbour lists) per-field parity after ONE step, also on a state squeezed
+    so hard that most particles exceed NBR_CAP = 96 neighbours (exercises the full-scan fallback)."""
+    for squeeze, min_nbrs in ((1.0, 0), (0.6, 96)):
+        sc = mixed_scene(with_dynamic=False)
+        if min_nbrs:
+            sc["Configuration"]["stiffness"] = 5  # rho ~ 3.7 rho0: keep (rho/rho0)^7 * k from ejecting the block
+        o, ps, solver = _pair(sc, seed=11, amp=0.002)
         fl = o.material == 1
         c = o.x[fl].mean(axis=0)
         o.x[fl] = ((o.x[fl] - c) * np.float32(squeeze) + c).astype(np.float32)
@@ -266,7 +269,8 @@ def test_fused_step_fields_vs_oracle_and_overflow_path():
         o.step(); solver.step()
         assert np.array_equal(ps.x_0.to_numpy(), o.x_0)
         if min_nbrs:
-            assert float(o.density[fl].max()) > 2000.0
+            assert float(o.density[fl].max()) > 3200.0
+            assert ps._engine.neighbor_stats()["overflow"] > 100
         assert _maxrel(ps.density.to_numpy(), o.density) < REL
         assert _maxrel(ps.pressure.to_numpy(), o.pressure) < 10 * REL
         assert _maxrel(ps.acceleration.to_numpy(), o.acceleration) < 10 * REL
