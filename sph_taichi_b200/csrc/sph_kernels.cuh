@@ -686,7 +686,10 @@ __device__ __forceinline__ void force_pair_pre(const DevParams &P, const DevArra
 #define WIN_CAP_VALUE 128
 #endif
 constexpr int WIN_CAP = WIN_CAP_VALUE;   // particles per staged window (2 KB); longer windows scan global memory
-constexpr int DENS_WARPS = 4;
+#ifndef DENS_WARPS_VALUE
+#define DENS_WARPS_VALUE 4
+#endif
+constexpr int DENS_WARPS = DENS_WARPS_VALUE;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
