@@ -353,3 +353,25 @@ def test_armadillo_bath_dynamic_full_size():
         dp = np.linalg.norm(p - p.mean(0), axis=1); dq = np.linalg.norm(q - q.mean(0), axis=1)
         assert np.abs(dp - dq).max() < 1e-4
         assert p[:, 1].mean() < q[:, 1].mean()  # and it is falling
+
+
+def test_two_fluid_densities_take_the_general_force_kernel():
+    """Two fluid blocks with different rest densities => non-uniform particle masses: the engine must drop
+    the uniform-fluid packing (48 B/neighbour general kernel, separate advect) and still match the oracle."""
+    from sph_taichi_b200 import scene
+    sc = scene.dam_break_box([8, 10, 8], domain_end=[0.6, 0.6, 0.5], start=[0.06, 0.06, 0.06])
+    second = dict(sc["FluidBlocks"][0])
+    second.update({"objectId": 1, "start": [0.06 + 8 * 0.02, 0.06, 0.06], "end": [0.06 + 13.5 * 0.02, 0.06 + 9.5 * 0.02, 0.06 + 7.5 * 0.02],
+                   "density": 800.0, "color": [200, 100, 50]})
+    sc["FluidBlocks"].append(second)
+    o, ps, solver = _pair(sc, seed=21, amp=0.002)
+    o.initialize(); solver.initialize()
+    steps = 20
+    for _ in range(steps):
+        o.step()
+    solver.step(steps)
+    assert len(np.unique(ps.m.to_numpy())) == 2
+    ko, kg = order_by_x0(o.x_0), order_by_x0(ps.x_0.to_numpy())
+    assert np.array_equal(ps.x_0.to_numpy()[kg], o.x_0[ko])
+    assert np.abs(ps.x.to_numpy()[kg] - o.x[ko]).max() / 0.02 < 1e-3
+    assert _maxrel(ps.density.to_numpy()[kg], o.density[ko]) < 1e-3
