@@ -186,7 +186,7 @@ int sph_slab_pair_times(SphCtx *ctx, int32_t enable, float *ms_out);
 int sph_read_status(SphCtx *ctx, uint32_t *status_out, void *stream); /* synchronises `stream` */
 int sph_clear_status(SphCtx *ctx, void *stream);
 /* neighbour-list statistics of the last density pass: out_dev4 = {max neighbours, particles in the
- * over-full fallback (> 64 neighbours), accepted pairs, fluid particles} */
+ * over-full fallback (> 96 neighbours), accepted pairs, fluid particles} */
 int sph_neighbor_stats(SphCtx *ctx, int32_t *out_dev4, void *stream);
 int64_t sph_particle_count(const SphCtx *ctx);
 /* number of kernels launched by this context since creation (graph replays counted per node) */
