@@ -25,7 +25,7 @@ enum { T_ZERO, T_HASH, T_SCAN, T_BUCKET, T_MOVE, T_BVOL, T_DENSITY, T_FORCE, T_A
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
-    uint64_t off_state[14];  // posm, veld, x0id, misc, acc (x2), aux, fpos, fvel, dfs
+    uint64_t off_state[14];  // posm, veld, x0id, misc, acc (x2), aux, fpv (2 slots, contiguous), dfs
     uint64_t off_cid, off_grid_ids, off_perm, off_ticket;
     uint64_t off_zero_begin, off_tile_counter, off_tile_state, off_cell_end, off_zero_end;
     uint64_t off_solid_slot, off_status, off_bodies, off_scratch, off_nbr_list, off_nbr_cnt;
@@ -39,7 +39,10 @@ Layout make_layout(int64_t n_max, int64_t C, int64_t n_solid, int n_bodies) {
     uint64_t o = 0;
     auto take = [&](uint64_t bytes) { uint64_t r = o; o = align_up(o + bytes, 256); return r; };
     uint64_t n = (uint64_t)(n_max > 0 ? n_max : 1);
-    for (int k = 0; k < 14; ++k) L.off_state[k] = take(n * sizeof(float4));
+    for (int k = 0; k < 14; ++k) {
+        if (k == 12) { L.off_state[k] = L.off_state[11] + n * sizeof(float4); continue; }  // second half of fpv
+        L.off_state[k] = take((k == 11 ? 2 : 1) * n * sizeof(float4));
+    }
     L.off_cid = take(n * 4);
     L.off_grid_ids = take(n * 4);
     L.off_perm = take(n * 4);
@@ -156,8 +159,7 @@ void bind_arrays(SphCtx *c) {
     int q = 1 - p;
     S.posm_n = st[0 + 5 * q]; S.veld_n = st[1 + 5 * q]; S.x0id_n = st[2 + 5 * q]; S.misc_n = st[3 + 5 * q]; S.acc_n = st[4 + 5 * q];
     S.aux = st[10];
-    S.fpos = st[11];
-    S.fvel = st[12];
+    S.fpv = st[11];  // 2 float4 per particle
     S.dfs = st[13];
     S.cid = reinterpret_cast<int32_t *>(w + L.off_cid);
     S.grid_ids = reinterpret_cast<int32_t *>(w + L.off_grid_ids);

@@ -47,10 +47,11 @@ struct DevArrays {
     float4 *posm, *veld, *x0id, *misc, *acc;       // current (sorted) state
     float4 *posm_n, *veld_n, *x0id_n, *misc_n, *acc_n;  // sort destination
     float4 *aux;
-    // per-step packed neighbour data of the uniform-fluid force pass (written by the density pass):
-    //   fpos = {x, y, z, fluid: m/rho_unclamped | solid: m_V}
-    //   fvel = {vx, vy, vz, fluid: p/rho^2 (>= 0) | solid: -body density (dynamic) or -inf (static)}
-    float4 *fpos, *fvel;
+    // per-step packed neighbour records of the uniform-fluid force pass (written by the density pass),
+    // 32 bytes per particle so that ONE 256-bit load (LDG.E.256) gathers a neighbour:
+    //   fpv[2i]     = {x, y, z, fluid: m/rho_unclamped | solid: m_V}
+    //   fpv[2i + 1] = {vx, vy, vz, fluid: p/rho^2 (>= 0) | solid: -body density (dynamic) or -inf (static)}
+    float4 *fpv;
     float4 *dfs;  // DFSPH: {dfsph_factor, density_adv, -, -} (particle_system.py:115-117)
     int32_t *cid;       // cell id per particle in pre-sort order
     int32_t *grid_ids;  // cell id per particle in sorted order (public grid_ids)
@@ -151,7 +152,14 @@ __device__ __forceinline__ float tait_pressure(const DevParams &P, float rho_cla
 // sorted arrays, so the walk is 9 contiguous index ranges.  Cells outside the grid are skipped
 // (SURVEY Q3); cell 0 is invisible exactly as in the reference (Q2) because a range always
 // starts at cell_end[max(c - 1, 0)].  fn(j, rx, ry, rz, r2, posm_j) is called for j != i, r2 < h2.
-template <typename F>
+// one 32-byte record with a single 256-bit read-only load (sm_100: LDG.E.256)
+__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
+template <int STRIDE = 1, typename F>
 __device__ __forceinline__ void for_all_neighbors(const DevParams &P, const float4 *__restrict__ posm,
                                                   const int32_t *__restrict__ cell_end, int i, float xi, float yi,
                                                   float zi, F &&fn) {
@@ -169,7 +177,7 @@ __device__ __forceinline__ void for_all_neighbors(const DevParams &P, const floa
             int j0 = __ldg(cell_end + max(c_lo - 1, 0));
             int j1 = __ldg(cell_end + c_hi);
             for (int j = j0; j < j1; ++j) {
-                float4 pj = __ldg(posm + j);
+                float4 pj = __ldg(posm + (size_t)j * STRIDE);
                 float rx = xi - pj.x, ry = yi - pj.y, rz = zi - pj.z;
                 float r2 = exact_r2(rx, ry, rz);
                 if (r2 < P.h2 && j != i) fn(j, rx, ry, rz, r2, pj);

@@ -770,8 +770,8 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
         if (!P.dfsph) S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
         S.nbr_cnt[i] = 0;
         if (P.uniform_fluid) {
-            S.fpos[i] = pi;  // w = m_V of the boundary particle
-            S.fvel[i] = make_float4(vb.x, vb.y, vb.z, dyn ? -vb.w : -__int_as_float(0x7f800000));
+            S.fpv[2 * (size_t)i] = pi;  // w = m_V of the boundary particle
+            S.fpv[2 * (size_t)i + 1] = make_float4(vb.x, vb.y, vb.z, dyn ? -vb.w : -__int_as_float(0x7f800000));
         }
     }
     if (__ballot_sync(0xffffffffu, fluid) == 0u) return;  // warp-uniform
@@ -910,8 +910,8 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
     S.aux[i] = make_float4(vol, dp, mi.x, 0.0f);
     if (P.uniform_fluid) {
         float4 vb = S.veld[i];
-        S.fpos[i] = make_float4(pi.x, pi.y, pi.z, vol);
-        S.fvel[i] = make_float4(vb.x, vb.y, vb.z, dp);
+        S.fpv[2 * (size_t)i] = make_float4(pi.x, pi.y, pi.z, vol);
+        S.fpv[2 * (size_t)i + 1] = make_float4(vb.x, vb.y, vb.z, dp);
     }
 }
 
@@ -964,7 +964,7 @@ __global__ void __launch_bounds__(THREADS) k_force_general(DevParams P, DevArray
     S.acc[i] = make_float4(A.npx + A.prx, A.npy + A.pry, A.npz + A.prz, 0.f);
 }
 
-// one accepted pair, uniform-fluid packing (see DevArrays::fpos / fvel)
+// one accepted pair, uniform-fluid packing (see DevArrays::fpv)
 __device__ __forceinline__ void force_pair_packed(const DevParams &P, const DevArrays &S, ForceAcc &A, int j, float rx,
                                                   float ry, float rz, float r2, const float4 &pj, const float4 &vj,
                                                   const float4 &vi, float dpi, float dpi_solid, float coh) {
@@ -993,8 +993,8 @@ __device__ __forceinline__ void force_pair_packed(const DevParams &P, const DevA
     }
 }
 
-// Fused force pass for uniform fluids: 2 x 16 B gathered per neighbour from the per-step copies
-// fpos / fvel.  Because nothing reads posm / veld of OTHER particles here, FUSE_ADVECT lets the
+// Fused force pass for uniform fluids: ONE 32-byte record gathered per neighbour (LDG.E.256) from the
+// per-step copy fpv.  Because nothing reads posm / veld of OTHER particles here, FUSE_ADVECT lets the
 // epilogue integrate the particle and clamp it to the walls in place (advect + enforce_boundary_3D
 // (fluid), WCSPH.py:143-149, sph_base.py:149-179) -- one launch and one pass over the state less.
 #ifndef FORCE_MIN_BLOCKS
@@ -1024,8 +1024,8 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
     uint32_t fl = __float_as_uint(mi.z);
     if (!(fl & FLAG_FLUID)) return;
     if (fl & FLAG_GHOST) return;
-    float4 pi = S.fpos[i];
-    float4 vi = S.fvel[i];
+    float4 pi, vi;
+    ldg256(S.fpv + 2 * (size_t)i, pi, vi);
     const float dpi = vi.w;
     const float dpi_solid = dpi + mi.y * P.inv_rho0sq;
     const float coh = P.sigma / mi.x * P.fluid_m;  // sigma / m_i * m_j
@@ -1040,10 +1040,7 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
             for (int u = 0; u < B; ++u) j[u] = (k0 + u < cnt) ? lp[(size_t)(k0 + u) * stride] : i;
             float4 pj[B], vj[B];
 #pragma unroll
-            for (int u = 0; u < B; ++u) {
-                pj[u] = __ldg(S.fpos + j[u]);
-                vj[u] = __ldg(S.fvel + j[u]);
-            }
+            for (int u = 0; u < B; ++u) ldg256(S.fpv + 2 * (size_t)j[u], pj[u], vj[u]);
 #pragma unroll
             for (int u = 0; u < B; ++u) {
                 float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
@@ -1052,11 +1049,12 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
             }
         }
     } else {
-        // full scan over the frozen copy fpos (posm may already hold advected neighbours)
-        for_all_neighbors(P, S.fpos, S.cell_end, i, pi.x, pi.y, pi.z,
-                          [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
-                              force_pair_packed(P, S, A, j, rx, ry, rz, r2, pj, __ldg(S.fvel + j), vi, dpi, dpi_solid, coh);
-                          });
+        // full scan over the frozen copy (posm may already hold advected neighbours)
+        for_all_neighbors<2>(P, S.fpv, S.cell_end, i, pi.x, pi.y, pi.z,
+                             [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
+                                 force_pair_packed(P, S, A, j, rx, ry, rz, r2, pj, __ldg(S.fpv + 2 * (size_t)j + 1), vi, dpi,
+                                                   dpi_solid, coh);
+                             });
     }
     float4 a = make_float4(A.npx + A.prx, A.npy + A.pry, A.npz + A.prz, 0.f);
     S.acc[i] = a;
