@@ -159,6 +159,14 @@ __device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
                  : "l"(p));
 }
 
+// streamed-once 32-bit load that does not allocate in L1 (neighbour-list entries must not evict the
+// gathered records)
+__device__ __forceinline__ int ldg_stream(const int32_t *p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 template <int STRIDE = 1, typename F>
 __device__ __forceinline__ void for_all_neighbors(const DevParams &P, const float4 *__restrict__ posm,
                                                   const int32_t *__restrict__ cell_end, int i, float xi, float yi,

@@ -1037,7 +1037,7 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
         for (int k0 = 0; k0 < cnt; k0 += B) {
             int j[B];
 #pragma unroll
-            for (int u = 0; u < B; ++u) j[u] = (k0 + u < cnt) ? lp[(size_t)(k0 + u) * stride] : i;
+            for (int u = 0; u < B; ++u) j[u] = (k0 + u < cnt) ? ldg_stream(lp + (size_t)(k0 + u) * stride) : i;
             float4 pj[B], vj[B];
 #pragma unroll
             for (int u = 0; u < B; ++u) ldg256(S.fpv + 2 * (size_t)j[u], pj[u], vj[u]);
