@@ -145,6 +145,8 @@ void derive_params(SphCtx *c) {
         if (q <= 0.5f) { float q2 = q * q; P.w_diam = h.k_w * (6.0f * q2 * q - 6.0f * q2 + 1.0f); }
         else { float f = 1.0f - q; if (f < 0) f = 0; P.w_diam = P.k2_w * (f * f * f); }
     }
+    P.k1_grad = P.k_dw * P.inv_h; P.wd_norm = P.w_diam / P.k2_w;
+    P.opaque_zero = 0;
     P.pad = h.h; P.hi_x = h.clamp_hi[0]; P.hi_y = h.clamp_hi[1]; P.hi_z = h.clamp_hi[2];
 }
 
@@ -231,8 +233,9 @@ int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *k
 void launch_pair_density(SphCtx *c, cudaStream_t st, int64_t *kernels) {
     const DevParams &P = c->P;
     const int blocks = blocks_for(P.n, DENS_WARPS * 32);
-    if (c->var_density == 0) k_density_tma<false><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
-    else k_density_tma<true><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
+    if (c->var_density == 0) k_density_tma<false, false><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
+    else if (P.dfsph || c->var_density == 2) k_density_tma<true, false><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
+    else k_density_tma<true, true><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
     *kernels += 1;
 }
 void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels,
@@ -318,6 +321,8 @@ int sph_create(const SphParams *params, int64_t n_max, int64_t n_solid, int32_t 
     int rc = validate_params(params, why);
     if (rc) return fail(nullptr, rc, why);
     if (n_max < 0 || n_max >= (1ll << 31) - 1) return fail(nullptr, SPH_E_CAPACITY, "n_max out of int32 range");
+    if ((uint64_t)align_up((uint64_t)(n_max > 0 ? n_max : 1), 32) * (uint64_t)NBR_CAP >= (1ull << 32))
+        return fail(nullptr, SPH_E_CAPACITY, "n_max too large: neighbour-list slots are 32-bit (NBR_CAP * n_max < 2^32)");
     if (n_solid < 0 || n_bodies < 0) return fail(nullptr, SPH_E_ARG, "negative capacity");
     if (!workspace) return fail(nullptr, SPH_E_ARG, "workspace is NULL");
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(nullptr, SPH_E_ARG, "workspace must be 256-byte aligned");

@@ -32,6 +32,7 @@ struct DevParams {
     float sigma, d_visc, visc_eps, dt;
     float gx_, gy_, gz_;
     float k_w, k2_w, k_dw, w0, w_diam;
+    float k1_grad, wd_norm;  // 6k / h and W(diameter) / 2k: normalisations of spline_pair()
     float pad, hi_x, hi_y, hi_z;
     // x-slab sharding (multi-GPU): this rank owns cell layers [sx0, sx1) and keeps sgw ghost
     // layers per side.  Records [n_local, n) were just received from the neighbour ranks.
@@ -41,6 +42,7 @@ struct DevParams {
     int32_t uniform_fluid;
     float fluid_m, fluid_mV;
     int32_t dfsph;  // simulationMethod 4: the density pass neither clamps nor evaluates the EOS
+    int32_t opaque_zero;  // always 0; lets a kernel state a scheduling dependency ptxas cannot fold away
 };
 
 struct DevArrays {
@@ -72,6 +74,7 @@ struct DevArrays {
 
 constexpr int NBR_CAP = 96;  // soak runs of the shipped scenes peak at 54 neighbours (tools/soak.py)
 constexpr int NBR_OVERFLOW = 0x7fffffff;
+constexpr int LIST_PAD = 4;  // lists are padded with the particle's own index to a multiple of this
 
 // |r|^2 in the reference's (and the oracle's) rounding sequence: three products, two sums, no FMA
 // contraction.  With P.h2 this makes the neighbour predicate `(x_i - x_j).norm() < h`
@@ -81,11 +84,51 @@ __device__ __forceinline__ float exact_r2(float rx, float ry, float rz) {
     return __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
 }
 
+// bare MUFU.RSQ / MUFU.RCP: rsqrtf() and __fdividef() without -ftz wrap the MUFU in a denormal
+// rescue (FMUL 2^24, FSETP, FSEL, FMUL 2^12 -- four extra issue slots per pair); squared distances
+// below 1.2e-38 m^2 do not occur and would flush to the r == 0 case, which is handled.
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // r = sqrt(r2) and 1/r from one MUFU.RSQ (|rel err| ~ 1e-7); exact 0 for coincident particles
 __device__ __forceinline__ void fast_norm(float r2, float &r, float &inv_r) {
-    float t = rsqrtf(r2);
+    float t = rsqrt_ftz(r2);
     inv_r = (r2 > 0.0f) ? t : 0.0f;
     r = r2 * inv_r;
+}
+
+// Branch-free cubic spline (sph_base.py:23-68) in the two-sided form
+//     W(q) = 2k (a^3 - 4 b^3),   dW/dq = 6k (4 b^2 - a^2),   a = max(1 - q, 0), b = max(1/2 - q, 0),
+// algebraically identical to the reference's piecewise polynomials (q <= 1/2: k(6q^3 - 6q^2 + 1) and
+// 6k q(3q - 2)); rounding differs by a few ulp of W(0).  Returns wn = W / (2k) and G with
+// grad W = (6k / h) * G * r_vec.  The reference's `r > 1e-5` guard on the gradient is applied to r^2;
+// below it r is treated as 0 (W(1e-5) and W(0) differ by 4e-7 relative).
+__device__ __forceinline__ void spline_pair(const DevParams &P, float r2, float &wn, float &G) {
+    float t = rsqrt_ftz(r2);
+    float inv_r = (r2 > 1e-10f) ? t : 0.0f;
+    float r = r2 * inv_r;
+    float a = fmaf(-r, P.inv_h, 1.0f);
+    float b = fmaxf(a - 0.5f, 0.0f);
+    a = fmaxf(a, 0.0f);
+    float a2 = a * a, b2 = b * b;
+    G = fmaf(4.0f, b2, -a2) * inv_r;
+    wn = fmaf(b2 * b, -4.0f, a2 * a);
+}
+// density-only variant: W / (2k)
+__device__ __forceinline__ float spline_w_norm(const DevParams &P, float r2) {
+    float r = r2 * rsqrt_ftz(fmaxf(r2, 1e-30f));  // exact 0 for coincident particles
+    float a = fmaf(-r, P.inv_h, 1.0f);
+    float b = fmaxf(a - 0.5f, 0.0f);
+    a = fmaxf(a, 0.0f);
+    return fmaf(b * b * b, -4.0f, a * a * a);
 }
 
 // grad W = s * r_vec, division-free variant of gradw_scale()

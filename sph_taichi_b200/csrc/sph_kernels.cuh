@@ -748,7 +748,9 @@ __device__ __forceinline__ uint32_t scan_chunk(const DevParams &P, const float4 
 #ifndef DENS_MIN_BLOCKS
 #define DENS_MIN_BLOCKS 9  // 56 registers: measured best (profiles/)
 #endif
-template <bool INLINE_W>
+// FASTW (with INLINE_W): the branch-free spline_w_norm() with the 2k factor applied once per particle;
+// DFSPH keeps the reference's piecewise form (its solver loops count iterations against the oracle).
+template <bool INLINE_W, bool FASTW>
 __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tma(DevParams P, DevArrays S) {
     __shared__ __align__(128) float4 s_win[DENS_WARPS][2][WIN_CAP + 32];
     __shared__ __align__(8) uint64_t s_bar[DENS_WARPS][2];
@@ -824,7 +826,9 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
                 S.nbr_list[widx] = jb + b;  // beyond NBR_CAP the last row is overwritten (flagged below)
                 widx = min(widx + (uint32_t)S.npad, widx_cap);
                 ++cnt;
-                if (INLINE_W) {
+                if (INLINE_W && FASTW) {
+                    den = fmaf(pj.w, spline_w_norm(P, r2), den);
+                } else if (INLINE_W) {
                     float r, inv_r;
                     fast_norm(r2, r, inv_r);
                     den += pj.w * w_cubic(P, r);
@@ -863,6 +867,9 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
 
     if (cnt <= NBR_CAP) {
         S.nbr_cnt[i] = cnt;
+        // pad the list to a multiple of LIST_PAD with the particle itself: the batched force pass then
+        // loads whole batches without per-entry predicates (a self pair contributes exactly zero)
+        for (int k = cnt; k & (LIST_PAD - 1); ++k) { S.nbr_list[widx] = i; widx += (uint32_t)S.npad; }
         if (!INLINE_W) {
             const size_t stride = (size_t)S.npad;
             const int32_t *lq = S.nbr_list + i;
@@ -894,7 +901,7 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
         }
     }
     float rho = pi.w * P.w0;
-    rho += den;
+    rho = (INLINE_W && FASTW) ? fmaf(den, P.k2_w, rho) : rho + den;
     rho *= P.rho0;
     float vol = mi.x / rho;  // m_j / rho_j with the UNCLAMPED density (viscosity)
     if (P.dfsph) {  // DFSPH.py:39-47: plain density, no clamp, no EOS
@@ -964,31 +971,38 @@ __global__ void __launch_bounds__(THREADS) k_force_general(DevParams P, DevArray
     S.acc[i] = make_float4(A.npx + A.prx, A.npy + A.pry, A.npz + A.prz, 0.f);
 }
 
-// one accepted pair, uniform-fluid packing (see DevArrays::fpv)
+// one accepted pair, uniform-fluid packing (see DevArrays::fpv).  Per-thread constants fold the spline
+// normalisations: grad W = K1 * G * r_vec, W = k2 * wn (spline_pair), so that cohesion, viscosity and
+// the pressure term (WCSPH.py:100-127, 55-85) collapse into ONE scalar s with a_i += s * r_vec.
+struct PackedConst {
+    float cohk;  // sigma / m_i * m_j * 2k  (cohesion uses W(max(r, d)), WCSPH.py:104-109)
+    float cp;    // rho0 * m_V of a fluid neighbour
+    float cps;   // rho0 * (p_i / rho_i^2 + p_i / rho0^2)  (solid neighbour, WCSPH.py:63)
+};
 __device__ __forceinline__ void force_pair_packed(const DevParams &P, const DevArrays &S, ForceAcc &A, int j, float rx,
                                                   float ry, float rz, float r2, const float4 &pj, const float4 &vj,
-                                                  const float4 &vi, float dpi, float dpi_solid, float coh) {
-    float r, inv_r;
-    fast_norm(r2, r, inv_r);
-    float gs = gradw_scale_fast(P, r, inv_r);
+                                                  const float4 &vi, float dpi, const PackedConst &K) {
+    float wn, G;
+    spline_pair(P, r2, wn, G);
+    const float g1 = G * P.k1_grad;
     if (vj.w >= 0.0f) {  // fluid neighbour: pj.w = m_j / rho_j, vj.w = p_j / rho_j^2
-        float w = (r2 > P.d2) ? w_cubic(P, r) : P.w_diam;
-        A.npx -= coh * rx * w; A.npy -= coh * ry * w; A.npz -= coh * rz * w;
+        wn = (r2 > P.d2) ? wn : P.wd_norm;
         float vxy = (vi.x - vj.x) * rx + (vi.y - vj.y) * ry + (vi.z - vj.z) * rz;
-        float sv = __fdividef(P.d_visc * pj.w * vxy, r * r + P.visc_eps) * gs;
-        A.npx += sv * rx; A.npy += sv * ry; A.npz += sv * rz;
-        float cp = -P.rho0 * P.fluid_mV * (dpi + vj.w) * gs;
-        A.prx += cp * rx; A.pry += cp * ry; A.prz += cp * rz;
+        float q1 = pj.w * vxy * rcp_ftz(r2 + P.visc_eps);
+        float tt = fmaf(q1, P.d_visc, -K.cp * (dpi + vj.w));
+        float s = fmaf(g1, tt, -K.cohk * wn);
+        A.npx = fmaf(s, rx, A.npx); A.npy = fmaf(s, ry, A.npy); A.npz = fmaf(s, rz, A.npz);
     } else {  // solid neighbour (Akinci 2012): pj.w = m_V_j, vj.w = -body density | -inf
-        float cp = -P.rho0 * pj.w * dpi_solid * gs;
+        float cp = -(K.cps * pj.w) * g1;
         float fx = cp * rx, fy = cp * ry, fz = cp * rz;
         A.prx += fx; A.pry += fy; A.prz += fz;
         float body_rho = -vj.w;
         if (body_rho < 3.0e38f) {  // dynamic rigid: reaction, WCSPH.py:66-68
             float *a = reinterpret_cast<float *>(S.acc + j);
-            atomicAdd(a + 0, -fx * P.rho0 / body_rho);
-            atomicAdd(a + 1, -fy * P.rho0 / body_rho);
-            atomicAdd(a + 2, -fz * P.rho0 / body_rho);
+            float sc = -P.rho0 * rcp_ftz(body_rho);
+            atomicAdd(a + 0, fx * sc);
+            atomicAdd(a + 1, fy * sc);
+            atomicAdd(a + 2, fz * sc);
         }
     }
 }
@@ -1009,6 +1023,7 @@ __device__ __forceinline__ void force_pair_packed(const DevParams &P, const DevA
 // split_info / split_mode (slab mode): process only the particles inside (mode 0) or outside (mode 1)
 // the index ranges this rank sends to its neighbours (info[1..8) / info[9..4), see k_slab_info), so
 // that the halo exchange of the next step can start while the interior is still being computed.
+static_assert(LIST_PAD % FORCE_BATCH == 0 && NBR_CAP % LIST_PAD == 0, "list padding must cover a force batch");
 template <int B, int THREADS, bool FUSE_ADVECT>
 __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevParams P, DevArrays S,
                                                                             const int32_t *__restrict__ split_info,
@@ -1027,25 +1042,37 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
     float4 pi, vi;
     ldg256(S.fpv + 2 * (size_t)i, pi, vi);
     const float dpi = vi.w;
-    const float dpi_solid = dpi + mi.y * P.inv_rho0sq;
-    const float coh = P.sigma / mi.x * P.fluid_m;  // sigma / m_i * m_j
+    PackedConst K;
+    K.cohk = P.sigma / mi.x * P.fluid_m * P.k2_w;  // sigma / m_i * m_j
+    K.cp = P.rho0 * P.fluid_mV;
+    K.cps = P.rho0 * (dpi + mi.y * P.inv_rho0sq);
     ForceAcc A = {P.gx_, P.gy_, P.gz_, 0.f, 0.f, 0.f};
     const int cnt = S.nbr_cnt[i];
     if (cnt != NBR_OVERFLOW) {
-        const int32_t *lp = S.nbr_list + i;
-        const size_t stride = (size_t)S.npad;
-        for (int k0 = 0; k0 < cnt; k0 += B) {
-            int j[B];
+        // 32-bit list slots (sph_create bounds NBR_CAP * npad below 2^32): one IADD + one IMAD.WIDE per load
+        const uint32_t np = (uint32_t)S.npad;
+        uint32_t slot = (uint32_t)i;
+        for (int k0 = 0; k0 < cnt; k0 += B, slot += B * np) {
+            int j[B];  // the density pass padded the list to a multiple of LIST_PAD with i itself
 #pragma unroll
-            for (int u = 0; u < B; ++u) j[u] = (k0 + u < cnt) ? ldg_stream(lp + (size_t)(k0 + u) * stride) : i;
+            for (int u = 0; u < B; ++u) j[u] = ldg_stream(S.nbr_list + (slot + (uint32_t)u * np));
             float4 pj[B], vj[B];
 #pragma unroll
             for (int u = 0; u < B; ++u) ldg256(S.fpv + 2 * (size_t)j[u], pj[u], vj[u]);
+            // all B gathers in flight before the first pair is evaluated: ptxas otherwise sinks three of
+            // them below the arithmetic of pair 0, which then stalls on the first record with nothing
+            // else outstanding.  (x | (y & 0)) with a zero it cannot see costs two LOP3 per batch.
+            {
+                uint32_t dep = 0u;
+#pragma unroll
+                for (int u = 1; u < B; ++u) dep ^= __float_as_uint(vj[u].w);
+                pj[0].x = __uint_as_float(__float_as_uint(pj[0].x) | (dep & (uint32_t)P.opaque_zero));
+            }
 #pragma unroll
             for (int u = 0; u < B; ++u) {
                 float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
                 float r2 = rx * rx + ry * ry + rz * rz;
-                force_pair_packed(P, S, A, j[u], rx, ry, rz, r2, pj[u], vj[u], vi, dpi, dpi_solid, coh);
+                force_pair_packed(P, S, A, j[u], rx, ry, rz, r2, pj[u], vj[u], vi, dpi, K);
             }
         }
     } else {
@@ -1053,7 +1080,7 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
         for_all_neighbors<2>(P, S.fpv, S.cell_end, i, pi.x, pi.y, pi.z,
                              [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
                                  force_pair_packed(P, S, A, j, rx, ry, rz, r2, pj, __ldg(S.fpv + 2 * (size_t)j + 1), vi, dpi,
-                                                   dpi_solid, coh);
+                                                   K);
                              });
     }
     float4 a = make_float4(A.npx + A.prx, A.npy + A.pry, A.npz + A.prz, 0.f);
