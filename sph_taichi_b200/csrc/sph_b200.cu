@@ -252,7 +252,7 @@ void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, in
         }
         return;
     }
-    if (P.uniform_fluid) k_force_packed<4, 128, false><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S, nullptr, 0);
+    if (P.uniform_fluid) k_force_packed<FORCE_BATCH, FORCE_THREADS, false><<<blocks_for(P.n, FORCE_THREADS), FORCE_THREADS, 0, st>>>(P, c->S, nullptr, 0);
     else k_force_general<4, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
     if (tm) tm->mark(T_ADVECT);
     k_advect<true><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);

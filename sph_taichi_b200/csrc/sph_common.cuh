@@ -74,7 +74,10 @@ struct DevArrays {
 
 constexpr int NBR_CAP = 96;  // soak runs of the shipped scenes peak at 54 neighbours (tools/soak.py)
 constexpr int NBR_OVERFLOW = 0x7fffffff;
-constexpr int LIST_PAD = 4;  // lists are padded with the particle's own index to a multiple of this
+#ifndef LIST_PAD_VALUE
+#define LIST_PAD_VALUE 4
+#endif
+constexpr int LIST_PAD = LIST_PAD_VALUE;  // lists are padded with the particle's own index to a multiple of this
 
 // |r|^2 in the reference's (and the oracle's) rounding sequence: three products, two sums, no FMA
 // contraction.  With P.h2 this makes the neighbour predicate `(x_i - x_j).norm() < h`

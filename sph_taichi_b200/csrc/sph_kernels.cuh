@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
         S.nbr_cnt[i] = cnt;
         // pad the list to a multiple of LIST_PAD with the particle itself: the batched force pass then
         // loads whole batches without per-entry predicates (a self pair contributes exactly zero)
-        for (int k = cnt; k & (LIST_PAD - 1); ++k) { S.nbr_list[widx] = i; widx += (uint32_t)S.npad; }
+        for (int k = cnt; k % LIST_PAD; ++k) { S.nbr_list[widx] = i; widx += (uint32_t)S.npad; }
         if (!INLINE_W) {
             const size_t stride = (size_t)S.npad;
             const int32_t *lq = S.nbr_list + i;
@@ -1052,13 +1052,14 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
         // 32-bit list slots (sph_create bounds NBR_CAP * npad below 2^32): one IADD + one IMAD.WIDE per load
         const uint32_t np = (uint32_t)S.npad;
         uint32_t slot = (uint32_t)i;
-        for (int k0 = 0; k0 < cnt; k0 += B, slot += B * np) {
+        for (int k0 = 0; k0 < cnt; k0 += B) {
             int j[B];  // the density pass padded the list to a multiple of LIST_PAD with i itself
-#pragma unroll
-            for (int u = 0; u < B; ++u) j[u] = ldg_stream(S.nbr_list + (slot + (uint32_t)u * np));
             float4 pj[B], vj[B];
 #pragma unroll
+            for (int u = 0; u < B; ++u) j[u] = ldg_stream(S.nbr_list + (slot + (uint32_t)u * np));
+#pragma unroll
             for (int u = 0; u < B; ++u) ldg256(S.fpv + 2 * (size_t)j[u], pj[u], vj[u]);
+            slot += B * np;
             // all B gathers in flight before the first pair is evaluated: ptxas otherwise sinks three of
             // them below the arithmetic of pair 0, which then stalls on the first record with nothing
             // else outstanding.  (x | (y & 0)) with a zero it cannot see costs two LOP3 per batch.
