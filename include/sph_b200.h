@@ -90,7 +90,9 @@ typedef struct SphRigidBody {
 typedef struct SphCtx SphCtx;
 
 /* ---- lifetime ------------------------------------------------------------------------ */
-/* Workspace bytes needed for n_max particles, n_solid solid particles, n_bodies bodies. */
+/* Workspace bytes needed for n_max particles, n_solid solid particles, n_bodies bodies.
+ * Capacity: 96 * round_up(n_max, 32) < 2^32 (per-step neighbour lists use 32-bit slots), i.e. n_max <= 44.7 M
+ * particles per GPU; sph_create returns SPH_E_CAPACITY beyond that (shard by x-slabs, sph_slab_*). */
 uint64_t sph_workspace_bytes(const SphParams *params, int64_t n_max, int64_t n_solid, int32_t n_bodies);
 int sph_create(const SphParams *params, int64_t n_max, int64_t n_solid, int32_t n_bodies, int32_t device,
                void *workspace, uint64_t workspace_bytes, SphCtx **out);

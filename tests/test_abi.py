@@ -63,3 +63,20 @@ def test_product_package_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f"{f} reaches into oracle/"
+
+
+def test_capacity_limit_is_reported_before_any_device_work():
+    """Neighbour-list slots are 32-bit: n_max beyond 2^32 / 96 is refused with SPH_E_CAPACITY (-3)."""
+    from sph_taichi_b200 import _lib
+    lib = _lib.load()
+    p = _lib.SphParams()
+    p.dim = 3
+    p.grid_num = (ctypes.c_int32 * 3)(8, 8, 8)
+    p.h = 0.04
+    p.density0 = 1000.0
+    h = ctypes.c_void_p()
+    ok_n, bad_n = 44_000_000, 45_000_000
+    assert lib.sph_workspace_bytes(ctypes.byref(p), ok_n, 0, 0) > 96 * 4 * ok_n
+    rc = lib.sph_create(ctypes.byref(p), bad_n, 0, 0, 0, None, 0, ctypes.byref(h))
+    assert rc < 0 and b"32-bit" in lib.sph_last_error(None), lib.sph_last_error(None)
+    assert not h.value
