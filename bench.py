@@ -184,6 +184,27 @@ def run_reference(args):
     return 0
 
 
+def pair_work(grid_ids, fluid_mask, grid_num, accepted_pairs):
+    """Compute-side work of ONE pass over the neighbourhood: candidate distance
+    tests = sum over fluid particles of the population of their 27-cell neighbourhood (cells outside the
+    grid skipped, cell 0 invisible as in the reference), and the accepted pairs the lists hold."""
+    import numpy as np
+    gx, gy, gz = (int(v) for v in grid_num)
+    cnt = np.bincount(grid_ids, minlength=gx * gy * gz).astype(np.int64)
+    cnt[0] = 0  # particle_system.py:383: the range of cell 0 is empty
+    c3 = cnt.reshape(gx, gy, gz)
+    pad = np.zeros((gx + 2, gy + 2, gz + 2), np.int64)
+    pad[1:-1, 1:-1, 1:-1] = c3
+    nb = np.zeros_like(c3)
+    for dx in range(3):
+        for dy in range(3):
+            for dz in range(3):
+                nb += pad[dx:dx + gx, dy:dy + gy, dz:dz + gz]
+    fluid_per_cell = np.bincount(grid_ids[fluid_mask], minlength=gx * gy * gz).astype(np.int64)
+    tests = int((fluid_per_cell * nb.reshape(-1)).sum())
+    return {"candidate_tests_per_pass": tests, "accepted_pairs_per_pass": int(accepted_pairs)}
+
+
 def run_single(args):
     import torch
     from sph_taichi_b200 import ParticleSystem, SimConfig
@@ -270,6 +291,19 @@ def run_single(args):
     e2e_s = time.perf_counter() - t0
     eng.check_status()
 
+    # ---- compute-side figure of the pair kernels (they are not HBM-bound) ----
+    compute = None
+    try:
+        stats = eng.neighbor_stats()
+        work = pair_work(ps.grid_ids.to_numpy(), ps.material.to_numpy() == 1, ps.grid_num, stats["pairs"])
+        sps = K / (cold_ms * 1e-3)
+        compute = dict(work, unit="per second, whole step (1 scan pass in the density kernel, 2 list passes)",
+                       candidate_tests_per_s=work["candidate_tests_per_pass"] * sps,
+                       interactions_per_s=2 * work["accepted_pairs_per_pass"] * sps,
+                       mean_neighbours=stats["mean"], max_neighbours=stats["max"])
+    except Exception as exc:  # diagnostics only: never lose the bench line over it
+        compute = {"error": str(exc)[:200]}
+
     cpu, _ = time_cpu_oracle(sc, budget_s=float(os.environ.get("SPH_BENCH_CPU_BUDGET_S", "15")))
 
     val = K / (cold_ms * 1e-3)
@@ -294,6 +328,7 @@ def run_single(args):
                 "pinned_copy_gbs_this_box": round(link_gbs, 2),
                 "note": "ParticleSystem.upload_state -> WCSPHSolver.step -> download_state, pinned host x and v"},
         "gpu_launches": int(launches),
+        "compute": compute,
         "roofline": {"kernel": "k_force<NP,PR> (fused non-pressure + pressure pass)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_force_traffic(name),
