@@ -160,6 +160,14 @@ def dragon_bath_dfsph():
     return _as_dfsph(dragon_bath())
 
 
+def dragon_bath_dynamic_dfsph():
+    """The reference's dragon_bath_dynamic_dfsph.json: the dragon is a dynamic (shape-matched) body."""
+    sc = dragon_bath_dfsph()
+    for body in sc["RigidBodies"]:
+        body["isDynamic"] = True
+    return sc
+
+
 def high_fluid_dfsph():
     return _as_dfsph(high_fluid_wcsph())
 
@@ -173,6 +181,7 @@ NAMED_SCENES = {
     "armadillo_bath_dynamic": armadillo_bath_dynamic,
     "high_fluid_wcsph": high_fluid_wcsph,
     "dragon_bath_dfsph": dragon_bath_dfsph,
+    "dragon_bath_dynamic_dfsph": dragon_bath_dynamic_dfsph,
     "high_fluid_dfsph": high_fluid_dfsph,
     "armadillo_bath_dynamic_dfsph": armadillo_bath_dynamic_dfsph,
     "cube_8k": cube_8k,
