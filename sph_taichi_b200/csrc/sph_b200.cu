@@ -119,36 +119,7 @@ int validate_params(const SphParams *p, std::string &why) {
     return SPH_OK;
 }
 
-void derive_params(SphCtx *c) {
-    const SphParams &h = c->hp;
-    DevParams &P = c->P;
-    P.gx = h.grid_num[0]; P.gy = h.grid_num[1]; P.gz = h.grid_num[2];
-    P.C = P.gx * P.gy * P.gz;
-    P.h = h.h; P.inv_h = 1.0f / h.h; P.d2 = h.diameter * h.diameter;
-    {   // h2 = min{t : sqrtf(t) >= h}: then r2 < h2 <=> sqrtf(r2) < h, the reference's predicate, exactly
-        float t = h.h * h.h;
-        while (std::sqrt(t) >= h.h) t = std::nextafter(t, 0.0f);
-        while (std::sqrt(std::nextafter(t, INFINITY)) < h.h) t = std::nextafter(t, INFINITY);
-        P.h2 = std::nextafter(t, INFINITY);
-        P.h2_scan = P.h2 * 1.000002f;  // FFMA-chain prefilter: a superset of the exact hits
-    }
-    P.m_V0 = h.m_V0; P.rho0 = h.density0; P.inv_rho0sq = 1.0f / (h.density0 * h.density0);
-    P.stiffness = h.stiffness; P.exponent = h.exponent;
-    float er = std::round(h.exponent);
-    P.exponent_int = (er == h.exponent && er >= 1.f && er <= 16.f) ? (int)er : 0;
-    P.sigma = h.surface_tension; P.d_visc = (float)(2.0 * (3 + 2) * (double)h.viscosity);
-    P.visc_eps = h.visc_eps; P.dt = h.dt;
-    P.gx_ = h.g[0]; P.gy_ = h.g[1]; P.gz_ = h.g[2];
-    P.k_w = h.k_w; P.k2_w = h.k_w * 2.0f; P.k_dw = h.k_dw; P.w0 = h.k_w;
-    {   // W(d) on the host with the same expression the device uses
-        float q = h.diameter * P.inv_h;
-        if (q <= 0.5f) { float q2 = q * q; P.w_diam = h.k_w * (6.0f * q2 * q - 6.0f * q2 + 1.0f); }
-        else { float f = 1.0f - q; if (f < 0) f = 0; P.w_diam = P.k2_w * (f * f * f); }
-    }
-    P.k1_grad = P.k_dw * P.inv_h; P.wd_norm = P.w_diam / P.k2_w;
-    P.opaque_zero = 0;
-    P.pad = h.h; P.hi_x = h.clamp_hi[0]; P.hi_y = h.clamp_hi[1]; P.hi_z = h.clamp_hi[2];
-}
+void derive_params(SphCtx *c) { derive_dev_params(c->P, c->hp); }
 
 void bind_arrays(SphCtx *c) {
     char *w = c->ws;

@@ -12,8 +12,15 @@
 //             flags = material | is_dynamic << 1 | color r,g,b << 8,16,24
 //   acc[i]  = {ax, ay, az, 0}                        (particle_system.py:106)
 #pragma once
+#ifdef SPH_EMU  // host-side emulation of the kernel source (tests/emu/): stand-ins for CUDA and the PTX helpers
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#include "sph_ptx.cuh"
+#endif
 #include <stdint.h>
+
+#include <cmath>
 
 #include "../../include/sph_b200.h"
 
@@ -85,20 +92,6 @@ constexpr int LIST_PAD = LIST_PAD_VALUE;  // lists are padded with the particle'
 // DFSPH counts neighbours (DFSPH.py:171-176).
 __device__ __forceinline__ float exact_r2(float rx, float ry, float rz) {
     return __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
-}
-
-// bare MUFU.RSQ / MUFU.RCP: rsqrtf() and __fdividef() without -ftz wrap the MUFU in a denormal
-// rescue (FMUL 2^24, FSETP, FSEL, FMUL 2^12 -- four extra issue slots per pair); squared distances
-// below 1.2e-38 m^2 do not occur and would flush to the r == 0 case, which is handled.
-__device__ __forceinline__ float rsqrt_ftz(float x) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_ftz(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
 }
 
 // r = sqrt(r2) and 1/r from one MUFU.RSQ (|rel err| ~ 1e-7); exact 0 for coincident particles
@@ -198,21 +191,6 @@ __device__ __forceinline__ float tait_pressure(const DevParams &P, float rho_cla
 // sorted arrays, so the walk is 9 contiguous index ranges.  Cells outside the grid are skipped
 // (SURVEY Q3); cell 0 is invisible exactly as in the reference (Q2) because a range always
 // starts at cell_end[max(c - 1, 0)].  fn(j, rx, ry, rz, r2, posm_j) is called for j != i, r2 < h2.
-// one 32-byte record with a single 256-bit read-only load (sm_100: LDG.E.256)
-__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                 : "l"(p));
-}
-
-// streamed-once 32-bit load that does not allocate in L1 (neighbour-list entries must not evict the
-// gathered records)
-__device__ __forceinline__ int ldg_stream(const int32_t *p) {
-    int v;
-    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-
 template <int STRIDE = 1, typename F>
 __device__ __forceinline__ void for_all_neighbors(const DevParams &P, const float4 *__restrict__ posm,
                                                   const int32_t *__restrict__ cell_end, int i, float xi, float yi,
@@ -238,4 +216,34 @@ __device__ __forceinline__ void for_all_neighbors(const DevParams &P, const floa
             }
         }
     }
+}
+
+// Host side: every derived constant the kernels read (particle_system.py:38,43-46; sph_base.py:23-68).
+inline void derive_dev_params(DevParams &P, const SphParams &h) {
+    P.gx = h.grid_num[0]; P.gy = h.grid_num[1]; P.gz = h.grid_num[2];
+    P.C = P.gx * P.gy * P.gz;
+    P.h = h.h; P.inv_h = 1.0f / h.h; P.d2 = h.diameter * h.diameter;
+    {   // h2 = min{t : sqrtf(t) >= h}: then r2 < h2 <=> sqrtf(r2) < h, the reference's predicate, exactly
+        float t = h.h * h.h;
+        while (std::sqrt(t) >= h.h) t = std::nextafter(t, 0.0f);
+        while (std::sqrt(std::nextafter(t, INFINITY)) < h.h) t = std::nextafter(t, INFINITY);
+        P.h2 = std::nextafter(t, INFINITY);
+        P.h2_scan = P.h2 * 1.000002f;  // FFMA-chain prefilter: a superset of the exact hits
+    }
+    P.m_V0 = h.m_V0; P.rho0 = h.density0; P.inv_rho0sq = 1.0f / (h.density0 * h.density0);
+    P.stiffness = h.stiffness; P.exponent = h.exponent;
+    float er = std::round(h.exponent);
+    P.exponent_int = (er == h.exponent && er >= 1.f && er <= 16.f) ? (int)er : 0;
+    P.sigma = h.surface_tension; P.d_visc = (float)(2.0 * (3 + 2) * (double)h.viscosity);
+    P.visc_eps = h.visc_eps; P.dt = h.dt;
+    P.gx_ = h.g[0]; P.gy_ = h.g[1]; P.gz_ = h.g[2];
+    P.k_w = h.k_w; P.k2_w = h.k_w * 2.0f; P.k_dw = h.k_dw; P.w0 = h.k_w;
+    {   // W(d) on the host with the same expression the device uses
+        float q = h.diameter * P.inv_h;
+        if (q <= 0.5f) { float q2 = q * q; P.w_diam = h.k_w * (6.0f * q2 * q - 6.0f * q2 + 1.0f); }
+        else { float f = 1.0f - q; if (f < 0) f = 0; P.w_diam = P.k2_w * (f * f * f); }
+    }
+    P.k1_grad = P.k_dw * P.inv_h; P.wd_norm = P.w_diam / P.k2_w;
+    P.opaque_zero = 0;
+    P.pad = h.h; P.hi_x = h.clamp_hi[0]; P.hi_y = h.clamp_hi[1]; P.hi_z = h.clamp_hi[2];
 }

@@ -681,7 +681,7 @@ __device__ __forceinline__ void force_pair_pre(const DevParams &P, const DevArra
     }
 }
 
-// ---- TMA / mbarrier primitives (sm_90+ PTX, sm_100a SASS: UBLKCP.S.G, SYNCS.ARRIVE.TRANS64) ----
+// ---- staging windows (the TMA / mbarrier primitives live in sph_ptx.cuh) ----
 #ifndef WIN_CAP_VALUE
 #define WIN_CAP_VALUE 128
 #endif
@@ -690,32 +690,6 @@ constexpr int WIN_CAP = WIN_CAP_VALUE;   // particles per staged window (2 KB); 
 #define DENS_WARPS_VALUE 4
 #endif
 constexpr int DENS_WARPS = DENS_WARPS_VALUE;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra.uni WAIT_DONE;\n"
-        "bra.uni WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 1-D bulk copy global -> shared::cta; bytes multiple of 16, both addresses 16-byte aligned
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 // Branch-free distance test of up to 32 candidates starting at jb.  d = |r|^2 - h^2 comes straight
 // out of a 3-FFMA chain and its sign bit is funnel-shifted into the mask (one SHF per candidate),
@@ -757,7 +731,7 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (lane == 0) { mbar_init(&s_bar[warp][0], 1); mbar_init(&s_bar[warp][1], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
     __syncwarp();
 
     bool live = i < P.n && !(P.slab_on && S.grid_ids[min(i, P.n - 1)] >= P.C);
