@@ -797,6 +797,7 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
             float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
             float r2 = exact_r2(rx, ry, rz);
             if (r2 < P.h2) {  // the exact `norm() < h` of the reference; the scan only pre-filters
+                SPH_EMU_CHECK((uint64_t)widx < (uint64_t)NBR_CAP * (uint64_t)S.npad && jb + b >= 0 && jb + b < P.n);
                 S.nbr_list[widx] = jb + b;  // beyond NBR_CAP the last row is overwritten (flagged below)
                 widx = min(widx + (uint32_t)S.npad, widx_cap);
                 ++cnt;
@@ -828,6 +829,7 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
             const float4 *w = &s_win[warp][b][0] - J0;
             for (int jb = j0; jb < j1; jb += 32) {
                 const int len = min(32, j1 - jb);
+                SPH_EMU_CHECK(jb >= J0 && jb + len - J0 <= WIN_CAP);  // inside the staged window
                 flush(scan_chunk<true>(P, w, jb, len, 0, pi.x, pi.y, pi.z), jb, len, w, true);
             }
         } else if (mode == 2) {
@@ -1031,6 +1033,8 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
             float4 pj[B], vj[B];
 #pragma unroll
             for (int u = 0; u < B; ++u) j[u] = ldg_stream(S.nbr_list + (slot + (uint32_t)u * np));
+#pragma unroll
+            for (int u = 0; u < B; ++u) SPH_EMU_CHECK(k0 + u < NBR_CAP && j[u] >= 0 && j[u] < P.n);  // padded with i
 #pragma unroll
             for (int u = 0; u < B; ++u) ldg256(S.fpv + 2 * (size_t)j[u], pj[u], vj[u]);
             slot += B * np;

@@ -375,3 +375,31 @@ def test_two_fluid_densities_take_the_general_force_kernel():
     assert np.array_equal(ps.x_0.to_numpy()[kg], o.x_0[ko])
     assert np.abs(ps.x.to_numpy()[kg] - o.x[ko]).max() / 0.02 < 1e-3
     assert _maxrel(ps.density.to_numpy()[kg], o.density[ko]) < 1e-3
+
+
+@pytest.mark.parametrize("seed,fill", [(21, 0.45), (22, 1.0)])
+def test_random_scatter_state_vs_oracle(seed, fill):
+    """Gas-like state: fluid particles scattered uniformly (about 1 per cell for fill = 0.45), so every kind
+    of candidate range occurs -- empty columns next to full ones, odd and even starts, windows of a few
+    particles -- next to a static block.  One fused step, field by field against the oracle."""
+    sc = mixed_scene(fluid_counts=(14, 14, 14), with_dynamic=False)
+    o, ps, solver = _pair(sc)
+    rng = np.random.default_rng(seed)
+    fl = o.material == 1
+    lo, hi = np.float32(0.05), np.float32(0.05 + 0.5 * fill)
+    o.x[fl] = rng.uniform(lo, hi, size=(int(fl.sum()), 3)).astype(np.float32)
+    o.v[fl] = rng.uniform(-1, 1, size=(int(fl.sum()), 3)).astype(np.float32)
+    ps.x.from_numpy(o.x)
+    ps.v.from_numpy(o.v)
+    o.initialize(); solver.initialize()
+    assert np.array_equal(ps.grid_particles_num.to_numpy(), o.grid_particles_num)
+    o.step(); solver.step()
+    assert ps._engine.check_status() == 0
+    assert np.array_equal(ps.x_0.to_numpy(), o.x_0)
+    assert _maxrel(ps.density.to_numpy(), o.density) < REL
+    assert _maxrel(ps.pressure.to_numpy(), o.pressure) < 10 * REL
+    assert _maxrel(ps.acceleration.to_numpy(), o.acceleration) < 10 * REL
+    assert _maxrel(ps.v.to_numpy(), o.v) < 10 * REL
+    # close random pairs give accelerations of 1e5 m/s^2: the position error is dt times the velocity error
+    dt = sc["Configuration"]["timeStepSize"]
+    assert np.abs(ps.x.to_numpy() - o.x).max() <= dt * 10 * REL * float(np.abs(o.v).max()) + 1e-6
