@@ -44,6 +44,46 @@ def install(lib_path):
 
     engine.Engine = EmuEngine
     torch.cuda.is_available = lambda: True
+
+    # the emulated runtime is synchronous: streams and events of the slab driver become no-ops
+    class _Stream:
+        cuda_stream = 0
+
+        def __init__(self, *a, **k):
+            pass
+
+        def wait_stream(self, *a):
+            pass
+
+        def wait_event(self, *a):
+            pass
+
+        def synchronize(self):
+            pass
+
+    class _Event:
+        def __init__(self, *a, **k):
+            pass
+
+        def record(self, *a):
+            pass
+
+        def wait(self, *a):
+            pass
+
+        def synchronize(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 0.0
+
+    import contextlib
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.set_device = lambda *a, **k: None
+    torch.cuda.current_stream = lambda *a, **k: _Stream()
+    torch.cuda.Stream = _Stream
+    torch.cuda.Event = _Event
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
     _init = particle_system.ParticleSystem.__init__
 
     def init_on_cpu(self, config, GGUI=False, device=None):

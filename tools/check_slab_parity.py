@@ -11,7 +11,13 @@ import json
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+EMU = os.environ.get("SPH_EMU_LIB")  # host-emulated library (tests/emu/): CPU tensors, gloo instead of NCCL
+if EMU:
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import emu_engine
+    emu_engine.install(EMU)
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -27,10 +33,13 @@ def main():
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", rank))
-    dev = torch.device(f"cuda:{local}")
+    dev = torch.device("cpu") if EMU else torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     if world > 1:
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        if EMU:
+            dist.init_process_group("gloo", rank=rank, world_size=world)
+        else:
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     d = 0.02
     c = a.counts
     sc = scene.dam_break_box(c, domain_end=[2.5 * c[0] * d + 0.2, c[1] * d + 0.4, c[2] * d + 0.12], start=[0.06] * 3)
