@@ -292,6 +292,16 @@ inline void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (((uint32_t)__atomic_load_n(bar, __ATOMIC_SEQ_CST) & 1u) == parity) std::this_thread::yield();
 }
 
+// packed fp32 pairs: two independent IEEE fp32 operations (lo = first element in memory)
+typedef unsigned long long f32x2;
+inline f32x2 pack2(float lo, float hi) { return ((f32x2)__float_as_uint(hi) << 32) | __float_as_uint(lo); }
+inline float emu_lo(f32x2 v) { return __uint_as_float((uint32_t)v); }
+inline float emu_hi(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+inline f32x2 add2(f32x2 a, f32x2 b) { return pack2(__fadd_rn(emu_lo(a), emu_lo(b)), __fadd_rn(emu_hi(a), emu_hi(b))); }
+inline f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    return pack2(std::fmaf(emu_lo(a), emu_lo(b), emu_lo(c)), std::fmaf(emu_hi(a), emu_hi(b), emu_hi(c)));
+}
+
 // ---- runtime API -----------------------------------------------------------------------------------------
 typedef int cudaError_t;
 constexpr cudaError_t cudaSuccess = 0;
