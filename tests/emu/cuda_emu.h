@@ -267,8 +267,21 @@ inline double atomicAdd(double *p, double v) {
 }
 
 // ---- stand-ins for sph_ptx.cuh ---------------------------------------------------------------------------
-inline float rsqrt_ftz(float x) { return 1.0f / std::sqrt(x); }
-inline float rcp_ftz(float x) { return 1.0f / x; }
+// SPH_EMU_MUFU_ULPS=n: perturb the results by a pseudo-random +-n ulp, the error class of MUFU.RSQ / MUFU.RCP
+// (tolerances of the parity tests must hold with it)
+#ifndef SPH_EMU_MUFU_ULPS
+#define SPH_EMU_MUFU_ULPS 0
+#endif
+inline float emu_mufu_noise(float y) {
+    if (SPH_EMU_MUFU_ULPS == 0 || !std::isfinite(y) || y == 0.0f) return y;
+    uint32_t b; std::memcpy(&b, &y, 4);
+    uint32_t h = (b * 2654435761u) >> 29;  // 0..7
+    b += (int)(h % (2 * SPH_EMU_MUFU_ULPS + 1)) - SPH_EMU_MUFU_ULPS;
+    std::memcpy(&y, &b, 4);
+    return y;
+}
+inline float rsqrt_ftz(float x) { return emu_mufu_noise(1.0f / std::sqrt(x)); }
+inline float rcp_ftz(float x) { return emu_mufu_noise(1.0f / x); }
 inline void ldg256(const float4 *p, float4 &a, float4 &b) { a = p[0]; b = p[1]; }
 inline int ldg_stream(const int32_t *p) { return *p; }
 // mbarrier: low word = completed phases, high word = bytes still expected in the current phase.  Only the
