@@ -231,6 +231,12 @@ inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 inline int __ffs(int x) { return __builtin_ffs(x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffsll(long long x) { return __builtin_ffsll(x); }
+inline unsigned __brev(unsigned x) {
+    unsigned r = 0;
+    for (int k = 0; k < 32; ++k) r |= ((x >> k) & 1u) << (31 - k);
+    return r;
+}
 inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) {
     uint64_t v = ((uint64_t)hi << 32) | lo;
     return (uint32_t)((v << (s & 31)) >> 32);
@@ -267,28 +273,26 @@ inline double atomicAdd(double *p, double v) {
 }
 
 // ---- stand-ins for sph_ptx.cuh ---------------------------------------------------------------------------
-// SPH_EMU_MUFU_ULPS=n: perturb the results by a pseudo-random +-n ulp, the error class of MUFU.RSQ / MUFU.RCP
-// (tolerances of the parity tests must hold with it)
-#ifndef SPH_EMU_MUFU_ULPS
-#define SPH_EMU_MUFU_ULPS 0
-#endif
-inline float emu_mufu_noise(float y) {
-    if (SPH_EMU_MUFU_ULPS == 0 || !std::isfinite(y) || y == 0.0f) return y;
-    uint32_t b; std::memcpy(&b, &y, 4);
-    uint32_t h = (b * 2654435761u) >> 29;  // 0..7
-    b += (int)(h % (2 * SPH_EMU_MUFU_ULPS + 1)) - SPH_EMU_MUFU_ULPS;
-    std::memcpy(&y, &b, 4);
-    return y;
-}
-inline float rsqrt_ftz(float x) { return emu_mufu_noise(1.0f / std::sqrt(x)); }
-inline float rcp_ftz(float x) { return emu_mufu_noise(1.0f / x); }
+inline float rsqrt_ftz(float x) { return 1.0f / std::sqrt(x); }
+inline float rcp_ftz(float x) { return 1.0f / x; }
 inline void ldg256(const float4 *p, float4 &a, float4 &b) { a = p[0]; b = p[1]; }
 inline int ldg_stream(const int32_t *p) { return *p; }
-// mbarrier: low word = completed phases, high word = bytes still expected in the current phase.  Only the
-// issuing lane writes; the waiting lanes poll.
+// mbarrier (arrival count 1): low word = completed phases, bits 32..62 = transaction count (signed: complete_tx may
+// run ahead of expect_tx), bit 63 = the arrive of the current phase has happened.  A phase completes when it has
+// arrived and its transaction count is zero.  Only the issuing lane writes; the waiting lanes poll.
+inline void emu_mbar_update(uint64_t *bar, int64_t tx_delta, bool arrive) {
+    uint64_t v = __atomic_load_n(bar, __ATOMIC_SEQ_CST);
+    uint32_t done = (uint32_t)v;
+    int64_t tx = (int64_t)((v >> 32) & 0x7fffffffull);
+    if (tx & 0x40000000) tx -= 0x80000000ll;  // sign-extend 31 bits
+    bool arrived = (v >> 63) != 0 || arrive;
+    tx += tx_delta;
+    if (arrived && tx == 0) { ++done; arrived = false; }
+    __atomic_store_n(bar, ((uint64_t)arrived << 63) | (((uint64_t)tx & 0x7fffffffull) << 32) | done, __ATOMIC_SEQ_CST);
+}
 inline void mbar_init(uint64_t *bar, int) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
 inline void mbar_fence_init() {}
-inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { __atomic_fetch_add(bar, (uint64_t)bytes << 32, __ATOMIC_SEQ_CST); }
+inline void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { emu_mbar_update(bar, (int64_t)bytes, true); }
 inline void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     if ((reinterpret_cast<uintptr_t>(dst_smem) | reinterpret_cast<uintptr_t>(src_gmem) | bytes) & 15u) {
         std::fprintf(stderr, "emu: cp.async.bulk needs 16-byte aligned addresses and size (dst %p src %p bytes %u)\n",
@@ -296,10 +300,7 @@ inline void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, u
         std::abort();
     }
     std::memcpy(dst_smem, src_gmem, bytes);
-    uint64_t v = __atomic_load_n(bar, __ATOMIC_SEQ_CST);
-    uint64_t pending = (v >> 32) - bytes;
-    uint64_t done = (v & 0xffffffffull) + (pending == 0 ? 1 : 0);
-    __atomic_store_n(bar, (pending << 32) | (done & 0xffffffffull), __ATOMIC_SEQ_CST);
+    emu_mbar_update(bar, -(int64_t)bytes, false);
 }
 inline void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (((uint32_t)__atomic_load_n(bar, __ATOMIC_SEQ_CST) & 1u) == parity) std::this_thread::yield();
