@@ -71,6 +71,10 @@ def build(src_dir=None, out=None, asan=False, defines=(), opt="-O1"):
     build_dir = os.path.join(HERE, "_build")
     os.makedirs(build_dir, exist_ok=True)
     out = out or os.path.join(build_dir, "libsph_b200_emu_asan.so" if asan else "libsph_b200_emu.so")
+    deps = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh"))]
+    deps += [os.path.join(HERE, "cuda_emu.h"), os.path.abspath(__file__), os.path.join(ROOT, "include", "sph_b200.h")]
+    if not defines and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out  # up to date (builds with extra -D always recompile)
     text = open(os.path.join(src_dir, "sph_b200.cu")).read()
     text, n = rewrite_launches(text)
     assert n > 20, f"only {n} kernel launches rewritten"
