@@ -1,11 +1,17 @@
 /*
  * sph_oracle.c -- CPU restatement of the reference WCSPH step (TEST INFRASTRUCTURE ONLY).
  *
- * PARITY UNPINNED: the reference (erizmr/SPH_Taichi @ 4a701fd) ships no tests, golden
- * vectors or fixtures, and cannot be executed here (taichi / trimesh / matplotlib are
- * not installed, there is no network).  This file restates the reference's algorithm
- * line by line; it is pinned only by closed-form known answers and by an independent
- * numpy restatement (oracle/np_ref.py), see tests/test_oracle.py.
+ * PARITY PIN: the reference (erizmr/SPH_Taichi @ 4a701fd) ships no tests, golden vectors or
+ * fixtures, and the Taichi wheel is not available here.  This file restates the reference's
+ * algorithm line by line and is pinned three ways:
+ *   (1) tests/test_golden_reference.py -- golden vectors written by the reference's OWN source
+ *       files (particle_system.py, sph_base.py, WCSPH.py, DFSPH.py, imported unmodified from
+ *       /root/reference) executed under a pure-Python stand-in for the Taichi runtime
+ *       (tests/golden/ti_shim/: serial loops, IEEE float32; tests/golden/make_reference_golden.py).
+ *       This pins the algorithm as written in the reference; it is NOT a run of Taichi's
+ *       code generator (fast-math, atomics order), which remains unavailable offline;
+ *   (2) closed-form known answers (tests/test_oracle.py);
+ *   (3) an independent all-pairs numpy restatement (oracle/np_ref.py).
  *
  * Nothing in the product path (sph_taichi_b200/) may import, link or call this file.
  * It is used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /

@@ -1,4 +1,5 @@
-"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE ONLY -- parity unpinned).
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE ONLY; pinned against the reference's own source run
+under a Taichi stand-in, tests/test_golden_reference.py -- see the header of sph_oracle.c).
 
 See ``sph_oracle.c`` for what is restated and from where.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may

@@ -1,7 +1,8 @@
 """Regenerate the committed golden vectors (run from the repo root: python tests/golden/make_golden.py).
 
 The reference cannot be executed offline (no taichi), so these vectors do NOT come from it: they are
-produced by the fp64 build of the CPU oracle (oracle/sph_oracle.c, parity unpinned) and serve as
+produced by the fp64 build of the CPU oracle (oracle/sph_oracle.c; the vectors that DO come from the reference's
+source are made by make_reference_golden.py) and serve as
 regression anchors for BOTH the fp32 oracle and the CUDA engine:
 
   dam_break_10x12x10_f64_40steps.npz   x_0 (float32 key), x, v (float64) after 40 WCSPH steps of a

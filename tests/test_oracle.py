@@ -1,4 +1,4 @@
-"""Pins for the CPU oracle (parity unpinned by the reference: it ships no tests).
+"""Pins for the CPU oracle besides tests/test_golden_reference.py (the reference ships no tests of its own).
 
 (i) closed-form known answers derived from the reference formulas;
 (ii) agreement with the independent all-pairs numpy restatement oracle/np_ref.py;
