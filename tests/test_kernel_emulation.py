@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
 
 FAST = ("neighbor_build_bit_exact or per_kernel_parity_mixed_scene or wall_clamp or overflow_path or "
         "stale_grid or out_of_grid or rigid_solve_recovers or random_scatter or (prefix_sum and not 200000) or "
-        "dfsph_per_kernel_parity or dfsph_kernels_on_overfull")
+        "dfsph_per_kernel_parity or dfsph_kernels_on_overfull or reproduces_the_reference_source")
 
 
 def _run(lib, extra_env=None, select=FAST):
@@ -25,12 +25,13 @@ def _run(lib, extra_env=None, select=FAST):
     env.pop("SPH_B200_LIB", None)
     env.update(extra_env or {})
     cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k", select,
-           os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_gpu_dfsph.py")]
+           os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_gpu_dfsph.py"),
+           os.path.join(ROOT, "tests", "test_gpu_reference_golden.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     tail = res.stdout[-3000:] + res.stderr[-3000:]
     assert res.returncode == 0, tail
     m = re.search(r"(\d+) passed", res.stdout)
-    assert m and int(m.group(1)) >= 12, tail
+    assert m and int(m.group(1)) >= 16, tail
     assert "skipped" not in res.stdout.splitlines()[-1], tail  # the emulation must actually run them
     return int(m.group(1))
 
