@@ -118,7 +118,11 @@ def run_reference(scene, steps, allow_oob=False):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(SCENES)
+    out_dir = HERE
+    args = sys.argv[1:]
+    if args[:1] == ["--out"]:
+        out_dir, args = args[1], args[2:]
+    names = args or list(SCENES)
     for name in names:
         scene, steps = SCENES[name]
         out = run_reference(json.loads(json.dumps(scene)), steps, allow_oob=(name == "wcsph_walls"))
@@ -128,8 +132,8 @@ if __name__ == "__main__":
             v = [int(t) for t in b["geometryFile"].split(":", 1)[1].split(",")]
             g = np.stack(np.meshgrid(*[np.arange(c) for c in v[:3]], indexing="ij"), -1).reshape(-1, 3) + np.array(v[3:6])
             fix = f"ref_{name}_body{b['objectId']}.npz"
-            np.savez_compressed(os.path.join(HERE, fix), pitch=np.float64(0.02), lattice=g.astype(np.int64))
+            np.savez_compressed(os.path.join(out_dir, fix), pitch=np.float64(0.02), lattice=g.astype(np.int64))
             b["geometryFile"] = "(synthetic lattice block)"
             b["voxelizedPointsFile"] = fix
-        np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), scene=json.dumps(mine), steps=steps, **out)
+        np.savez_compressed(os.path.join(out_dir, f"ref_{name}.npz"), scene=json.dumps(mine), steps=steps, **out)
         print(name, "particles", len(out["final_x"]), "steps", steps)
