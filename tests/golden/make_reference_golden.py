@@ -63,6 +63,9 @@ SCENES = {
                           FluidBlocks=[fluid([0.10, 0.06, 0.10], (6, 7, 6), (0.0, -1.0, 0.0))],
                           RigidBodies=[body(1, (4, 4, 4), (6, 11, 6), True, (0.5, -2.0, 0.0), 700.0),
                                        body(2, (3, 5, 6), (12, 3, 5), False)]), 7),
+    # the 1 200-particle dam break of tests/golden/dam_break_*: 40 steps, two wall contacts, an evolving free surface
+    "wcsph_dambreak": (dict(Configuration=base_cfg(domain=(0.8, 0.6, 0.4)),
+                            FluidBlocks=[fluid([0.05, 0.05, 0.05], (10, 12, 10), (0.0, 0.0, 0.0))]), 40),
     # DFSPH (divergence + pressure solver loops of the reference, host-side convergence tests)
     "dfsph_blocks": (dict(Configuration=base_cfg(method=4, dt=0.004),
                           FluidBlocks=[fluid([0.10, 0.06, 0.10], (5, 7, 6), (2.0, -1.0, 0.0)),
@@ -125,7 +128,7 @@ if __name__ == "__main__":
     names = args or list(SCENES)
     for name in names:
         scene, steps = SCENES[name]
-        out = run_reference(json.loads(json.dumps(scene)), steps, allow_oob=(name == "wcsph_walls"))
+        out = run_reference(json.loads(json.dumps(scene)), steps, allow_oob=(name in ("wcsph_walls", "wcsph_dambreak")))
         # the oracle / engine side reads rigid bodies from a lattice fixture instead of a mesh
         mine = json.loads(json.dumps(scene))
         for k, b in enumerate(mine.get("RigidBodies", [])):

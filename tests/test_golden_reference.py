@@ -61,7 +61,7 @@ def test_oracle_reproduces_the_reference_source(name):
 
 
 def test_reference_goldens_cover_both_solvers_and_rigid_bodies():
-    assert {"wcsph_blocks", "wcsph_walls", "wcsph_bodies", "dfsph_blocks"} <= set(NAMES)
+    assert {"wcsph_blocks", "wcsph_walls", "wcsph_bodies", "wcsph_dambreak", "dfsph_blocks"} <= set(NAMES)
 
 
 def test_committed_goldens_regenerate_from_the_reference(tmp_path):
