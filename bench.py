@@ -329,7 +329,7 @@ def run_single(args):
                 "note": "ParticleSystem.upload_state -> WCSPHSolver.step -> download_state, pinned host x and v"},
         "gpu_launches": int(launches),
         "compute": compute,
-        "roofline": {"kernel": "k_force<NP,PR> (fused non-pressure + pressure pass)", "bound": "hbm",
+        "roofline": {"kernel": "k_force_packed<4,128,true> (fused cohesion + viscosity + pressure gradient + integration)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_force_traffic(name),
                      "peak_source": peak_src, "algorithmic_bytes_per_particle": FORCE_BYTES_PER_PARTICLE,
