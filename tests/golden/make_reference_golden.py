@@ -71,6 +71,10 @@ SCENES = {
                           FluidBlocks=[fluid([0.10, 0.06, 0.10], (5, 7, 6), (2.0, -1.0, 0.0)),
                                        fluid([0.21, 0.06, 0.10], (5, 7, 6), (-2.0, -1.0, 0.0), oid=3)],
                           RigidBlocks=[block(1, [0.32, 0.06, 0.10], (3, 5, 6), False)]), 4),
+    # DFSPH with a dynamic RigidBlock: the reaction terms of the solver sweeps on dynamic solid particles
+    "dfsph_dynamic_block": (dict(Configuration=base_cfg(method=4, dt=0.004),
+                                 FluidBlocks=[fluid([0.10, 0.06, 0.10], (6, 6, 6), (0.0, -1.5, 0.0))],
+                                 RigidBlocks=[block(1, [0.12, 0.19, 0.12], (4, 3, 4), True, (0.0, -2.5, 0.0), 500.0)]), 3),
 }
 FIELDS = ("object_id", "x_0", "x", "v", "acceleration", "m_V", "m", "density", "pressure", "material", "is_dynamic",
           "grid_ids")
