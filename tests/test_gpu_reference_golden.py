@@ -44,10 +44,13 @@ def test_engine_reproduces_the_reference_source(name):
         # Shape matching sums in a different order than the reference's serial loops (fp64 moments on the GPU), so a
         # body particle within 1e-7 of a cell face may sort into the neighbouring cell: for scenes with dynamic
         # bodies the particles are matched by their immutable (object id, x_0) key after the first step.
-        loose = stage == "final_" and any(b["isDynamic"] for b in scene.get("RigidBodies", []))
         got = {f: getattr(ps, f).to_numpy() for f in ("object_id", "material", "is_dynamic", "grid_ids", "x_0", "x", "v",
                                                        "m_V", "density", "pressure", "acceleration")}
         want = {f: z[stage + f] for f in got}
+        # ... and, on any scene, a particle within an ulp of a cell face may do the same once approximate rsqrt / rcp
+        # are in play: the init stage is always exact, later stages fall back to the key match if the order differs
+        loose = stage == "final_" and (any(b["isDynamic"] for b in scene.get("RigidBodies", []))
+                                       or not np.array_equal(got["x_0"], want["x_0"]))
         if loose:
             kg = np.lexsort((got["x_0"][:, 2], got["x_0"][:, 1], got["x_0"][:, 0], got["object_id"]))
             kw = np.lexsort((want["x_0"][:, 2], want["x_0"][:, 1], want["x_0"][:, 0], want["object_id"]))
