@@ -66,6 +66,10 @@ SCENES = {
     # the 1 200-particle dam break of tests/golden/dam_break_*: 40 steps, two wall contacts, an evolving free surface
     "wcsph_dambreak": (dict(Configuration=base_cfg(domain=(0.8, 0.6, 0.4)),
                             FluidBlocks=[fluid([0.05, 0.05, 0.05], (10, 12, 10), (0.0, 0.0, 0.0))]), 40),
+    # BASELINE configs[0]: the 8 K cube (20^3 lattice in the unit box) -- about 80 s per step in pure Python, so only
+    # a few steps; only x_0 / x / v / density of the final state are kept (SMALL below)
+    "wcsph_cube8k": (dict(Configuration=base_cfg(domain=(1.0, 1.0, 1.0)),
+                          FluidBlocks=[dict(fluid([0.1, 0.1, 0.1], (20, 20, 20)), end=[0.49, 0.49, 0.49])]), 6),
     # DFSPH (divergence + pressure solver loops of the reference, host-side convergence tests)
     "dfsph_blocks": (dict(Configuration=base_cfg(method=4, dt=0.004),
                           FluidBlocks=[fluid([0.10, 0.06, 0.10], (5, 7, 6), (2.0, -1.0, 0.0)),
@@ -76,6 +80,7 @@ SCENES = {
                                  FluidBlocks=[fluid([0.10, 0.06, 0.10], (6, 6, 6), (0.0, -1.5, 0.0))],
                                  RigidBlocks=[block(1, [0.12, 0.19, 0.12], (4, 3, 4), True, (0.0, -2.5, 0.0), 500.0)]), 3),
 }
+SMALL = ("wcsph_cube8k",)
 FIELDS = ("object_id", "x_0", "x", "v", "acceleration", "m_V", "m", "density", "pressure", "material", "is_dynamic",
           "grid_ids")
 
@@ -142,5 +147,9 @@ if __name__ == "__main__":
             np.savez_compressed(os.path.join(out_dir, fix), pitch=np.float64(0.02), lattice=g.astype(np.int64))
             b["geometryFile"] = "(synthetic lattice block)"
             b["voxelizedPointsFile"] = fix
+        if name in SMALL:  # keep the committed file small: final state only, the fields a trajectory pin needs
+            keep = ("final_object_id", "final_x_0", "final_x", "final_v", "final_density", "final_grid_ids",
+                    "final_grid_particles_num", "oob_cell_reads", "dfsph_iterations_v", "dfsph_iterations")
+            out = {k: v for k, v in out.items() if k in keep}
         np.savez_compressed(os.path.join(out_dir, f"ref_{name}.npz"), scene=json.dumps(mine), steps=steps, **out)
         print(name, "particles", len(out["final_x"]), "steps", steps)

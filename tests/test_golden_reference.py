@@ -46,18 +46,20 @@ def test_oracle_reproduces_the_reference_source(name):
             if dfsph:  # the host-side convergence loops stop after the same number of sweeps
                 assert [a for a, _ in its] == list(z["dfsph_iterations_v"]), (its, z["dfsph_iterations_v"])
                 assert [b for _, b in its] == list(z["dfsph_iterations"]), (its, z["dfsph_iterations"])
+        if stage + "x" not in z.files:  # the 8 K cube keeps the final state only (file size)
+            continue
         # the reference's own particle order and integer data: exact
-        for f in ("object_id", "material", "is_dynamic", "grid_ids"):
-            assert np.array_equal(getattr(o, f), z[stage + f]), (stage, f)
-        assert np.array_equal(o.grid_particles_num, z[stage + "grid_particles_num"]), stage
-        assert np.array_equal(o.x_0, z[stage + "x_0"]), stage
+        for f in ("object_id", "material", "is_dynamic", "grid_ids", "grid_particles_num", "x_0"):
+            if stage + f in z.files:
+                assert np.array_equal(getattr(o, f), z[stage + f]), (stage, f)
         for f in ("x", "v", "m_V", "m", "density", "pressure", "acceleration"):
-            _close(getattr(o, f), z[stage + f], what=f"{name} {stage}{f}")
+            if stage + f in z.files:
+                _close(getattr(o, f), z[stage + f], what=f"{name} {stage}{f}")
         if dfsph:
             fl = o.material == 1
             _close(o.dfsph_factor[fl], z[stage + "dfsph_factor"][fl], 1e-4, f"{name} {stage}dfsph_factor")
             _close(o.density_adv[fl], z[stage + "density_adv"][fl], what=f"{name} {stage}density_adv")
-    assert steps >= 3 and len(o.x) > 200
+    assert steps >= 3 and len(o.x) > 200 and "final_x" in z.files
 
 
 def test_reference_goldens_cover_both_solvers_and_rigid_bodies():

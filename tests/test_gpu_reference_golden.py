@@ -41,11 +41,14 @@ def test_engine_reproduces_the_reference_source(name):
                 assert max(abs(a - int(b)) for (a, _), b in zip(its, z["dfsph_iterations_v"])) <= 1
                 assert max(abs(a - int(b)) for (_, a), b in zip(its, z["dfsph_iterations"])) <= 1
         assert ps._engine.check_status() == 0
+        if stage + "x" not in z.files:  # the 8 K cube keeps the final state only
+            continue
         # Shape matching sums in a different order than the reference's serial loops (fp64 moments on the GPU), so a
         # body particle within 1e-7 of a cell face may sort into the neighbouring cell: for scenes with dynamic
         # bodies the particles are matched by their immutable (object id, x_0) key after the first step.
         got = {f: getattr(ps, f).to_numpy() for f in ("object_id", "material", "is_dynamic", "grid_ids", "x_0", "x", "v",
-                                                       "m_V", "density", "pressure", "acceleration")}
+                                                       "m_V", "density", "pressure", "acceleration")
+               if stage + f in z.files}
         want = {f: z[stage + f] for f in got}
         # ... and, on any scene, a particle within an ulp of a cell face may do the same once approximate rsqrt / rcp
         # are in play: the init stage is always exact, later stages fall back to the key match if the order differs
@@ -61,8 +64,10 @@ def test_engine_reproduces_the_reference_source(name):
             assert np.array_equal(got["grid_ids"], want["grid_ids"]), stage
             assert np.array_equal(ps.grid_particles_num.to_numpy(), z[stage + "grid_particles_num"]), stage
         for f in ("object_id", "material", "is_dynamic", "x_0"):
-            assert np.array_equal(got[f], want[f]), (stage, f)
+            if f in got:
+                assert np.array_equal(got[f], want[f]), (stage, f)
         tol = 50 * REL if dfsph else REL
         for f, k in (("x", 1), ("v", 5), ("m_V", 1), ("density", 1), ("pressure", 10), ("acceleration", 10)):
-            err = _rel(got[f], want[f])
-            assert err < k * tol, f"{name} {stage}{f}: {err:.3e}"
+            if f in got:
+                err = _rel(got[f], want[f])
+                assert err < k * tol, f"{name} {stage}{f}: {err:.3e}"
