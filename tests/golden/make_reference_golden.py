@@ -79,6 +79,10 @@ SCENES = {
     "dfsph_dynamic_block": (dict(Configuration=base_cfg(method=4, dt=0.004),
                                  FluidBlocks=[fluid([0.10, 0.06, 0.10], (6, 6, 6), (0.0, -1.5, 0.0))],
                                  RigidBlocks=[block(1, [0.12, 0.19, 0.12], (4, 3, 4), True, (0.0, -2.5, 0.0), 500.0)]), 3),
+    # DFSPH with a shape-matched rigid BODY (the situation of the reference's dragon_bath_dynamic_dfsph.json)
+    "dfsph_bodies": (dict(Configuration=base_cfg(method=4, dt=0.004),
+                          FluidBlocks=[fluid([0.10, 0.06, 0.10], (6, 6, 6), (0.0, -1.0, 0.0))],
+                          RigidBodies=[body(1, (4, 3, 4), (6, 10, 6), True, (0.3, -2.0, 0.0), 600.0)]), 3),
 }
 SMALL = ("wcsph_cube8k",)
 FIELDS = ("object_id", "x_0", "x", "v", "acceleration", "m_V", "m", "density", "pressure", "material", "is_dynamic",
