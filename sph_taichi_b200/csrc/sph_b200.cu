@@ -486,11 +486,12 @@ int sph_enforce_boundary(SphCtx *ctx, int32_t particle_type, void *stream) {
 int sph_set_rigid_bodies(SphCtx *ctx, const SphRigidBody *bodies, int32_t n_bodies) {
     if (!ctx || n_bodies < 0 || (n_bodies > 0 && !bodies)) return SPH_E_ARG;
     if (n_bodies > ctx->body_cap) return fail(ctx, SPH_E_CAPACITY, "more rigid bodies than the workspace was sized for");
+    for (int b = 0; b < n_bodies; ++b)  // validate everything before any state changes
+        if (bodies[b].solid_begin < 0 || bodies[b].solid_end < bodies[b].solid_begin || bodies[b].solid_end > ctx->n_solid_cap)
+            return fail(ctx, SPH_E_ARG, "rigid body solid-id range out of bounds");
     ctx->bodies.assign(bodies, bodies + n_bodies);
     std::vector<RigidBodyDev> h(n_bodies);
     for (int b = 0; b < n_bodies; ++b) {
-        if (bodies[b].solid_begin < 0 || bodies[b].solid_end < bodies[b].solid_begin || bodies[b].solid_end > ctx->n_solid_cap)
-            return fail(ctx, SPH_E_ARG, "rigid body solid-id range out of bounds");
         std::memset(&h[b], 0, sizeof(RigidBodyDev));
         h[b].object_id = bodies[b].object_id;
         h[b].solid_begin = bodies[b].solid_begin;
@@ -508,7 +509,7 @@ static int rigid_call(SphCtx *ctx, int32_t body, int mode, float *out, void *str
     if (body < 0 || body >= (int)ctx->bodies.size()) return fail(ctx, SPH_E_ARG, "rigid body index out of range");
     k_rigid<<<1, RIGID_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S, dev_bodies(ctx), body, mode, out);
     ctx->launches += 1;
-    if (mode == 2) ctx->built = false; ctx->list_valid = false;
+    if (mode == 2) { ctx->built = false; ctx->list_valid = false; }  // modes 0 / 1 only read
     CUDA_TRY(ctx, cudaGetLastError());
     return SPH_OK;
 }

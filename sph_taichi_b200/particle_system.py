@@ -133,16 +133,38 @@ class ParticleSystem:
             start += cnt
 
     # ------------------------------------------------------------------------------------
+    def _solver_constants(self):
+        """The constants the reference bakes into its kernels from the SOLVER's attributes at first launch
+        (sph_base.py:13-21, WCSPH.py:9-14): assigning ``solver.viscosity = ...`` etc. takes effect here too
+        (at the next engine call; the reference honours it only before its first kernel compile)."""
+        cfg, s = self.cfg, getattr(self, "_solver", None)
+
+        def pick(attr, default):
+            v = getattr(s, attr, None) if s is not None else None
+            return default if v is None else v
+
+        g = pick("g", cfg.get_cfg("gravitation"))
+        return (float(pick("density_0", cfg.get_cfg("density0") or 1000.0)),
+                float(pick("stiffness", cfg.get_cfg("stiffness") or 50000.0)),
+                float(pick("exponent", cfg.get_cfg("exponent") or 7.0)),
+                tuple(float(v) for v in np.asarray(g, dtype=np.float64).reshape(-1)),
+                float(pick("viscosity", 0.01)), float(pick("surface_tension", 0.01)))
+
     def _make_params(self, dt=None):
-        cfg = self.cfg
-        return _engine.make_params(
-            self.dim, self.grid_num, self.particle_radius, cfg.get_cfg("density0") or 1000.0,
-            cfg.get_cfg("stiffness") or 50000.0, cfg.get_cfg("exponent") or 7.0,
-            self._dt if dt is None else dt, cfg.get_cfg("gravitation"), self.domain_size)
+        rho0, stiff, expo, g, visc, sigma = self._solver_constants()
+        return _engine.make_params(self.dim, self.grid_num, self.particle_radius, rho0, stiff, expo,
+                                   self._dt if dt is None else dt, g, self.domain_size,
+                                   viscosity=visc, surface_tension=sigma)
+
+    def _sync_params(self):
+        key = (self._dt,) + self._solver_constants()
+        if key != getattr(self, "_param_key", None):
+            self._engine.set_params(self._make_params())
+            self._param_key = key
 
     def _set_dt(self, dt):
         self._dt = float(dt)
-        self._engine.set_params(self._make_params())
+        self._sync_params()
 
     # ---- field <-> engine coherence -----------------------------------------------------
     def _pull(self, field=None):
@@ -163,6 +185,7 @@ class ParticleSystem:
 
     def _push(self):
         """Make the engine state current before an engine call."""
+        self._sync_params()
         if self._fields_dirty:
             n = int(self.particle_num[None])
             self._prepare_solids(n)

@@ -15,6 +15,7 @@ from .fields import ScalarField
 class SPHBase:
     def __init__(self, particle_system):
         self.ps = particle_system
+        self.ps._solver = self  # the engine constants follow this object's attributes (ps._solver_constants)
         self.g = np.array(self.ps.cfg.get_cfg("gravitation"))
         self.viscosity = 0.01      # sph_base.py:15
         self.density_0 = self.ps.cfg.get_cfg("density0")
