@@ -17,7 +17,9 @@ from sph_taichi_b200 import ParticleSystem, SimConfig
 
 def write_ply_ascii(path, pos):
     with open(path, "w") as fh:
-        fh.write("ply\nformat ascii 1.0\n")
+        # header as ti.tools.PLYWriter.export_frame_ascii prints it (comment line included; restated from the
+        # Taichi docs, the wheel is not installable offline)
+        fh.write("ply\nformat ascii 1.0\ncomment created by PLYWriter\n")
         fh.write(f"element vertex {pos.shape[0]}\nproperty float x\nproperty float y\nproperty float z\nend_header\n")
         np.savetxt(fh, pos, fmt="%.7g")
 

@@ -29,6 +29,7 @@ struct Layout {
     uint64_t off_cid, off_grid_ids, off_perm, off_ticket;
     uint64_t off_zero_begin, off_tile_counter, off_tile_state, off_cell_end, off_zero_end;
     uint64_t off_solid_slot, off_status, off_bodies, off_scratch, off_nbr_list, off_nbr_cnt;
+    uint64_t off_soa[3];
     int64_t npad;
     uint64_t total;
     int n_tiles;
@@ -61,6 +62,7 @@ Layout make_layout(int64_t n_max, int64_t C, int64_t n_solid, int n_bodies) {
     L.npad = (int64_t)align_up(n, 32);
     L.off_nbr_cnt = take((uint64_t)L.npad * 4);
     L.off_nbr_list = take((uint64_t)L.npad * 4 * NBR_CAP);
+    for (int a = 0; a < 3; ++a) L.off_soa[a] = take((uint64_t)(L.npad + 32) * 4);  // +32: the scan reads whole groups of 8
     L.total = o;
     return L;
 }
@@ -146,6 +148,9 @@ void bind_arrays(SphCtx *c) {
     S.nbr_list = reinterpret_cast<int32_t *>(w + L.off_nbr_list);
     S.nbr_cnt = reinterpret_cast<int32_t *>(w + L.off_nbr_cnt);
     S.npad = (int32_t)L.npad;
+    S.sx = reinterpret_cast<float *>(w + L.off_soa[0]);
+    S.sy = reinterpret_cast<float *>(w + L.off_soa[1]);
+    S.sz = reinterpret_cast<float *>(w + L.off_soa[2]);
 }
 
 inline RigidBodyDev *dev_bodies(SphCtx *c) { return reinterpret_cast<RigidBodyDev *>(c->ws + c->L.off_bodies); }
@@ -204,7 +209,12 @@ int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *k
 void launch_pair_density(SphCtx *c, cudaStream_t st, int64_t *kernels) {
     const DevParams &P = c->P;
     const int blocks = blocks_for(P.n, DENS_WARPS * 32);
-    if (c->var_density == 0) k_density_tma<false, false><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
+    if (c->var_density == 10) {  // v10: SoA quads, no staging
+        const int b10 = blocks_for(P.n, DENS10_THREADS);
+        if (P.dfsph) k_density_soa<false><<<b10, DENS10_THREADS, 0, st>>>(P, c->S);
+        else k_density_soa<true><<<b10, DENS10_THREADS, 0, st>>>(P, c->S);
+    }
+    else if (c->var_density == 0) k_density_tma<false, false><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
     else if (P.dfsph || c->var_density == 2) k_density_tma<true, false><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
     else k_density_tma<true, true><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
     *kernels += 1;

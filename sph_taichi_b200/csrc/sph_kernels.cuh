@@ -262,7 +262,9 @@ __global__ void k_rank_move(DevParams P, DevArrays S) {
         dst = a + rank;
     }
     float4 misc = S.misc[src];
-    S.posm_n[dst] = S.posm[src];
+    const float4 pm = S.posm[src];
+    S.posm_n[dst] = pm;
+    S.sx[dst] = pm.x; S.sy[dst] = pm.y; S.sz[dst] = pm.z;
     S.veld_n[dst] = S.veld[src];
     S.x0id_n[dst] = S.x0id[src];
     S.misc_n[dst] = misc;
@@ -878,6 +880,221 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
     }
     float rho = pi.w * P.w0;
     rho = (INLINE_W && FASTW) ? fmaf(den, P.k2_w, rho) : rho + den;
+    rho *= P.rho0;
+    float vol = mi.x / rho;  // m_j / rho_j with the UNCLAMPED density (viscosity)
+    if (P.dfsph) {  // DFSPH.py:39-47: plain density, no clamp, no EOS
+        reinterpret_cast<float *>(S.veld + i)[3] = rho;
+        S.aux[i] = make_float4(vol, 0.0f, mi.x, 0.0f);
+        return;
+    }
+    float rc = fmaxf(rho, P.rho0);
+    float p = tait_pressure(P, rc);
+    float dp = p / (rc * rc);
+    reinterpret_cast<float *>(S.veld + i)[3] = rc;
+    reinterpret_cast<float *>(S.misc + i)[1] = p;
+    S.aux[i] = make_float4(vol, dp, mi.x, 0.0f);
+    if (P.uniform_fluid) {
+        float4 vb = S.veld[i];
+        S.fpv[2 * (size_t)i] = make_float4(pi.x, pi.y, pi.z, vol);
+        S.fpv[2 * (size_t)i + 1] = make_float4(vb.x, vb.y, vb.z, dp);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Density pass v10: SoA candidate quads, one coalesced cell_end load per column.
+//
+// What the v8 profile showed (profiles/r02_density_v8_source_breakdown.txt): per warp 5266 instructions =
+// 670 per-column set-up (18 dependent cell_end loads, 2 CREDUX, spilled window state) + 1937 scan + 2065 hit
+// loop; and the L1/shared pipe at 80 %: an AoS LDS.128 per candidate costs 5.8 wavefronts because the lanes
+// of a warp sit in 4-5 cells whose windows start ~128 bytes apart (same banks).  Here:
+//  * positions are read from the per-step SoA rows sx / sy / sz (k_rank_move writes them): one 128-bit load
+//    per row delivers FOUR consecutive candidates, the lanes' addresses are ~32 bytes apart (different banks /
+//    one or two L1 lines), 0.75 loads per candidate instead of 1;
+//  * a warp's 32 consecutive particles sit in ONE (x, y) column of cells (fast path, checked): the cell_end
+//    entries all lanes need for a neighbour column are `span + 3` consecutive words -- one coalesced load by
+//    the first lanes, each lane picks its two range ends with shuffles; the next column's load is issued
+//    before the current column is processed;
+//  * no staging: the windows of a warp are ~6 KB and stay in L1; TMA copies of ~200 bytes each cost more
+//    issue slots than they hide latency (profiles/r02_parked_variants_sweep.txt).
+// Output (lists, densities, EOS, fpv) is identical to k_density_tma: same candidates, same visiting order.
+#ifndef DENS10_THREADS
+#define DENS10_THREADS 128
+#endif
+#ifndef DENS10_MIN_BLOCKS
+#define DENS10_MIN_BLOCKS 8
+#endif
+#ifndef DENS10_PACKED
+#define DENS10_PACKED 0  // 1: FADD2 / FFMA2 on the (x, y) (z, w) halves of a quad
+#endif
+#ifndef DENS10_SYMMETRIC
+#define DENS10_SYMMETRIC 0  // 1: visit the columns as corners, centre, edges (list order only; sums within tolerance)
+#endif
+__device__ __forceinline__ int dens10_column(int p) {
+#if DENS10_SYMMETRIC
+    return (int)((0x753148620ull >> (4 * p)) & 15ull);  // 0, 2, 6, 8, 4, 1, 3, 5, 7
+#else
+    return p;
+#endif
+}
+__device__ __forceinline__ float4 ldg_quad(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// distance pre-filter of up to 32 candidates jb .. jb + len - 1 (jb a multiple of 4), eight per step:
+// candidate u ends up in bit len - 1 - u (the sign of |r|^2 - h2_scan is funnel-shifted in)
+__device__ __forceinline__ uint32_t scan_soa(const DevParams &P, const float *__restrict__ sx,
+                                             const float *__restrict__ sy, const float *__restrict__ sz, int jb, int len,
+                                             float xi, float yi, float zi) {
+    uint32_t m = 0u;
+    int done = 0;
+#if DENS10_PACKED
+    const f32x2 nx = pack2(-xi, -xi), ny = pack2(-yi, -yi), nz = pack2(-zi, -zi), nh = pack2(-P.h2_scan, -P.h2_scan);
+#endif
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (g * 8 < len) {
+            const float4 X0 = ldg_quad(sx + jb + g * 8), X1 = ldg_quad(sx + jb + g * 8 + 4);
+            const float4 Y0 = ldg_quad(sy + jb + g * 8), Y1 = ldg_quad(sy + jb + g * 8 + 4);
+            const float4 Z0 = ldg_quad(sz + jb + g * 8), Z1 = ldg_quad(sz + jb + g * 8 + 4);
+#if DENS10_PACKED
+            auto two = [&](float xa, float xb, float ya, float yb, float za, float zb) {
+                f32x2 rx = add2(pack2(xa, xb), nx), ry = add2(pack2(ya, yb), ny), rz = add2(pack2(za, zb), nz);
+                f32x2 d = fma2(rz, rz, fma2(ry, ry, fma2(rx, rx, nh)));
+                m = __funnelshift_l((uint32_t)d, m, 1);
+                m = __funnelshift_l((uint32_t)(d >> 32), m, 1);
+            };
+            two(X0.x, X0.y, Y0.x, Y0.y, Z0.x, Z0.y); two(X0.z, X0.w, Y0.z, Y0.w, Z0.z, Z0.w);
+            two(X1.x, X1.y, Y1.x, Y1.y, Z1.x, Z1.y); two(X1.z, X1.w, Y1.z, Y1.w, Z1.z, Z1.w);
+#else
+            auto one = [&](float x, float y, float z) {
+                float rx = xi - x, ry = yi - y, rz = zi - z;
+                float d = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, -P.h2_scan)));
+                m = __funnelshift_l(__float_as_uint(d), m, 1);
+            };
+            one(X0.x, Y0.x, Z0.x); one(X0.y, Y0.y, Z0.y); one(X0.z, Y0.z, Z0.z); one(X0.w, Y0.w, Z0.w);
+            one(X1.x, Y1.x, Z1.x); one(X1.y, Y1.y, Z1.y); one(X1.z, Y1.z, Z1.z); one(X1.w, Y1.w, Z1.w);
+#endif
+            done = g * 8 + 8;
+        }
+    }
+    return m >> (done - len);
+}
+
+template <bool FASTW>
+__global__ void __launch_bounds__(DENS10_THREADS, DENS10_MIN_BLOCKS) k_density_soa(DevParams P, DevArrays S) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = i < P.n && !(P.slab_on && S.grid_ids[min(i, P.n - 1)] >= P.C);
+    float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), mi = pi;
+    uint32_t fl = 0;
+    if (live) { pi = S.posm[i]; mi = S.misc[i]; fl = __float_as_uint(mi.z); }
+    const bool fluid = live && (fl & FLAG_FLUID);
+    if (live && !fluid) {
+        bool dyn = (fl & FLAG_DYNAMIC) != 0;
+        float4 vb = S.veld[i];
+        S.aux[i] = make_float4(vb.w, 0.0f, dyn ? -2.0f : -1.0f, 0.0f);
+        if (!P.dfsph) S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        S.nbr_cnt[i] = 0;
+        if (P.uniform_fluid) {
+            S.fpv[2 * (size_t)i] = pi;  // w = m_V of the boundary particle
+            S.fpv[2 * (size_t)i + 1] = make_float4(vb.x, vb.y, vb.z, dyn ? -vb.w : -__int_as_float(0x7f800000));
+        }
+    }
+    if (__ballot_sync(0xffffffffu, fluid) == 0u) return;  // warp-uniform
+
+    int ci = 0, cj = 0, ck = 0;
+    cell_of(P, pi.x, pi.y, pi.z, ci, cj, ck);
+    ci = min(max(ci, 0), P.gx - 1); cj = min(max(cj, 0), P.gy - 1); ck = min(max(ck, 0), P.gz - 1);
+    const int k_lo = max(ck - 1, 0), k_hi = min(ck + 1, P.gz - 1);
+    // fast path: all fluid lanes in one (x, y) column of cells and few enough z-cells for one load per column
+    const int colkey = ci * P.gy + cj;
+    const int key_lo = __reduce_min_sync(0xffffffffu, fluid ? colkey : 0x7fffffff);
+    const int key_hi = __reduce_max_sync(0xffffffffu, fluid ? colkey : -1);
+    const int kmin = __reduce_min_sync(0xffffffffu, fluid ? ck : 0x7fffffff);
+    const int kmax = __reduce_max_sync(0xffffffffu, fluid ? ck : -1);
+    const bool fast = key_lo == key_hi && kmax - kmin + 4 <= 32;
+    const int ci_u = key_lo / P.gy, cj_u = key_lo - ci_u * P.gy;
+    // fast path: lane L holds cell_end[row_c + kmin - 2 + L] of the column being prepared; a lane's range ends are
+    // entries k_lo - kmin + 1 and k_hi - kmin + 2 (particle_system.py:383: [prefix[max(c_lo - 1, 0)], prefix[c_hi]))
+    auto col_entry = [&](int c) -> int {
+        const int ni = ci_u + c / 3 - 1, nj = cj_u + c % 3 - 1;
+        if (ni < 0 || ni >= P.gx || nj < 0 || nj >= P.gy) return -1;  // column outside the grid: empty range
+        const int row = (ni * P.gy + nj) * P.gz;
+        const int idx = min(max(row + kmin - 2 + lane, 0), row + P.gz - 1);
+        return __ldg(S.cell_end + idx);
+    };
+    auto col_range_slow = [&](int c, int &j0, int &j1) {
+        int ni = ci + c / 3 - 1, nj = cj + c % 3 - 1;
+        j0 = 0; j1 = 0;
+        if (fluid && ni >= 0 && ni < P.gx && nj >= 0 && nj < P.gy) {
+            int row = (ni * P.gy + nj) * P.gz;
+            j0 = __ldg(S.cell_end + max(row + k_lo - 1, 0));
+            j1 = __ldg(S.cell_end + row + k_hi);
+        }
+    };
+
+    int cnt = 0;
+    float den = 0.0f;
+    uint32_t widx = (uint32_t)(fluid ? i : 0);  // index of the next list slot
+    const uint32_t widx_cap = widx + (uint32_t)(NBR_CAP - 1) * (uint32_t)S.npad;  // last row
+    auto flush = [&](uint32_t m, int jb, int len) {
+        if ((uint32_t)(i - jb) < (uint32_t)len) m &= ~(1u << (len - 1 - (i - jb)));  // p_i != p_j
+        while (m) {
+            int hb = 31 - __clz(m);  // highest set bit = earliest candidate: keeps the reference order
+            m &= ~(1u << hb);
+            int j = jb + len - 1 - hb;
+            SPH_EMU_CHECK(j >= 0 && j < P.n);
+            float4 pj = __ldg(S.posm + j);
+            float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+            float r2 = exact_r2(rx, ry, rz);
+            if (r2 < P.h2) {  // the exact `norm() < h` of the reference; the scan only pre-filters
+                SPH_EMU_CHECK((uint64_t)widx < (uint64_t)NBR_CAP * (uint64_t)S.npad);
+                S.nbr_list[widx] = j;  // beyond NBR_CAP the last row is overwritten (flagged below)
+                widx = min(widx + (uint32_t)S.npad, widx_cap);
+                ++cnt;
+                if (FASTW) {
+                    den = fmaf(pj.w, spline_w_norm(P, r2), den);
+                } else {
+                    float r, inv_r;
+                    fast_norm(r2, r, inv_r);
+                    den += pj.w * w_cubic(P, r);
+                }
+            }
+        }
+    };
+
+    int e_next = fast ? col_entry(dens10_column(0)) : 0;
+    for (int p = 0; p < 9; ++p) {
+        const int c = dens10_column(p);
+        int j0, j1;
+        if (fast) {
+            const int e = e_next;
+            if (p + 1 < 9) e_next = col_entry(dens10_column(p + 1));
+            j0 = __shfl_sync(0xffffffffu, e, k_lo - kmin + 1);
+            j1 = __shfl_sync(0xffffffffu, e, k_hi - kmin + 2);
+            if (!fluid || e < 0) { j0 = 0; j1 = 0; }  // e < 0 is warp-uniform (column outside the grid)
+        } else {
+            col_range_slow(c, j0, j1);
+        }
+        if (j1 <= j0) continue;
+        const int a0 = j0 & ~3;  // quads are 16-byte aligned: up to 3 candidates below the range are scanned and dropped
+        for (int jb = a0; jb < j1; jb += 32) {
+            const int len = min(32, j1 - jb);
+            uint32_t m = scan_soa(P, S.sx, S.sy, S.sz, jb, len, pi.x, pi.y, pi.z);
+            if (jb < j0) m &= 0xffffffffu >> (32 - len + (j0 - jb));  // candidates jb .. j0 - 1 are the top bits
+            flush(m, jb, len);
+        }
+    }
+    if (!fluid) return;
+
+    if (cnt <= NBR_CAP) {
+        S.nbr_cnt[i] = cnt;
+        // pad the list to a multiple of LIST_PAD with the particle itself: the batched force pass then
+        // loads whole batches without per-entry predicates (a self pair contributes exactly zero)
+        for (int k = cnt; k % LIST_PAD; ++k) { S.nbr_list[widx] = i; widx += (uint32_t)S.npad; }
+    } else {
+        S.nbr_cnt[i] = NBR_OVERFLOW;
+    }
+    float rho = pi.w * P.w0;
+    rho = FASTW ? fmaf(den, P.k2_w, rho) : rho + den;
     rho *= P.rho0;
     float vol = mi.x / rho;  // m_j / rho_j with the UNCLAMPED density (viscosity)
     if (P.dfsph) {  // DFSPH.py:39-47: plain density, no clamp, no EOS

@@ -234,6 +234,55 @@ def test_dump_and_invariants_dragon_bath_full_size():
     assert rho.min() >= 1000.0 and rho.max() < 1300.0
 
 
+def test_dragon_bath_full_size_against_oracle():
+    """BASELINE cfg 2 at FULL size (441 996 particles), field by field against the oracle, particles matched
+    by their immutable key (object id, x_0).  The engine first runs 320 steps (the column falls 0.06 m and hits
+    the floor: clamps, pressure and viscosity are all active); that state is handed to the oracle and both
+    advance 8 more steps."""
+    from oracle.sph_oracle import OracleSim
+    from sph_taichi_b200 import ParticleSystem, SimConfig, scene
+    sc = scene.dragon_bath()
+    ps = ParticleSystem(SimConfig(sc))
+    solver = ps.build_solver()
+    solver.initialize()
+    o = OracleSim(sc)
+    o.initialize()
+
+    def keys(x0, oid):
+        return np.lexsort((x0[:, 2], x0[:, 1], x0[:, 0], oid))
+
+    solver.step(320)
+    x0, oid = ps.x_0.to_numpy(), ps.object_id.to_numpy()
+    kg, ko = keys(x0, oid), keys(o.x_0, o.object_id)
+    assert np.array_equal(x0[kg], o.x_0[ko]) and np.array_equal(oid[kg], o.object_id[ko])
+    o.x[ko] = ps.x.to_numpy()[kg]
+    o.v[ko] = ps.v.to_numpy()[kg]
+    steps = 8
+    solver.step(steps)
+    for _ in range(steps):
+        o.step()
+    assert ps._engine.check_status() == 0
+    x, x0, oid = ps.x.to_numpy(), ps.x_0.to_numpy(), ps.object_id.to_numpy()
+    kg, ko = keys(x0, oid), keys(o.x_0, o.object_id)
+    assert np.array_equal(x0[kg], o.x_0[ko]) and np.array_equal(oid[kg], o.object_id[ko])
+    fl = o.material[ko] == 1
+    d = 0.02
+    # the state is not at rest: pressure, wall contacts and a spread of densities
+    assert float(o.pressure.max()) > 1000.0 and float(o.density[o.material == 1].max()) > 1010.0
+    assert (o.x[ko][fl][:, 1] <= np.float32(0.04)).sum() > 1000
+    got = {"dx_over_d": float(np.abs(x[kg] - o.x[ko]).max() / d),          # positions, in particle diameters
+           "v": _maxrel(ps.v.to_numpy()[kg], o.v[ko]),
+           "density": _maxrel(ps.density.to_numpy()[kg], o.density[ko]),
+           "pressure": _maxrel(ps.pressure.to_numpy()[kg], o.pressure[ko]),   # (rho / rho0)^7 amplifies 7x
+           "acceleration": _maxrel(ps.acceleration.to_numpy()[kg], o.acceleration[ko]),
+           # same cell for (all but face-sitting) particles => both hold the same stable counting sort
+           "cell_mismatch": float((ps.grid_ids.to_numpy()[kg] != o.grid_ids[ko]).mean())}
+    tol = {"dx_over_d": 1e-4, "v": 1e-4, "density": REL, "pressure": 50 * REL, "acceleration": 50 * REL,
+           "cell_mismatch": 1e-5}
+    print("dragon_bath full size vs oracle:", got)
+    assert all(got[k] < tol[k] for k in tol), (got, tol)
+
+
 def test_stale_grid_is_refused():
     o, ps, solver = _pair(mixed_scene())
     solver.initialize()
