@@ -27,6 +27,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# the CPU arm: pin the OpenMP threads (must be set before libgomp initialises); the thread COUNT is chosen below
+os.environ.setdefault("OMP_PROC_BIND", "close")
+os.environ.setdefault("OMP_PLACES", "cores")
 
 METRIC = "M particle-updates/sec (SPH steps/sec x particles)"
 UNIT = "M particle-updates/s"
@@ -41,6 +44,21 @@ def scene_for(n_gpus, name=None):
     return name, scene.NAMED_SCENES[name]()
 
 
+def workload_config(name, sc, particles, fluid_particles):
+    """The `config` object -- identical (keys AND values) in the B200 arm and in the --impl reference arm."""
+    import numpy as np
+    c = sc["Configuration"]
+    ds = np.array(c["domainEnd"], dtype=np.float64) - np.array(c["domainStart"], dtype=np.float64)
+    cells = int(np.prod(np.ceil(ds / (4.0 * c["particleRadius"])).astype(int)))
+    return {"workload": name, "particles": int(particles), "fluid_particles": int(fluid_particles), "grid_cells": cells,
+            "solver": "WCSPH" if c["simulationMethod"] == 0 else "DFSPH", "dt": c["timeStepSize"],
+            "state": "the scene after `warmup` steps from its initial lattice",
+            "l2": "B200 arm: L2 flushed between timed steps at N = 1 (256 MiB write; 'steady' is un-flushed), per-rank "
+                  "working set > L2 at N > 1; reference arm: CPU caches not flushed",
+            "parallelism": "B200 arm: N = 1 single GPU, N > 1 x-slabs with one halo exchange per step; reference arm: "
+                           "OpenMP over the host cores"}
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -50,14 +68,40 @@ def measured_hbm_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_force_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the force kernel, per launch, from the committed
-    ncu --set full capture of the same workload (profiles/force_dram_traffic.json), else None."""
+def ncu_dram_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one kernel, per launch, from this round's committed
+    ncu --set full capture of the same workload (profiles/dram_traffic.json names the capture), else None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "force_dram_traffic.json")) as fh:
-            return json.load(fh).get(workload, {}).get("bytes_per_launch")
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as fh:
+            return json.load(fh).get(workload, {}).get(kernel)
     except Exception:
         return None
+
+
+# algorithmic bytes per particle and launch (SURVEY.md section 8d) and the compute-side model of the pair kernels:
+# fp32 lane-operations = candidate tests x 7 (3 FADD + 3 FFMA + 1 SHF) + accepted pairs x the SASS instructions of
+# one pair (density hit 30, force pair 54), against SMs x 128 fp32 lanes x the SM clock seen during the run
+ALGO_BYTES = {"density": 24, "force": FORCE_BYTES_PER_PARTICLE}
+LANE_OPS_PER_TEST, LANE_OPS_PER_DENSITY_HIT, LANE_OPS_PER_FORCE_PAIR = 7, 30, 54
+KERNEL_NAME = {"density": "density pass (k_density_*: scan + neighbour lists + EOS)",
+               "force": "k_force_packed<4,128,true> (cohesion + viscosity + pressure gradient + integration + walls)"}
+
+
+def roofline_entry(kind, workload, n, launch_ms, total_ms, peak, work, sm_mhz):
+    ach = ALGO_BYTES[kind] * n / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
+    e = {"kernel": KERNEL_NAME[kind], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+         "frac": ach / peak, "traffic": ncu_dram_traffic(workload, kind),
+         "algorithmic_bytes_per_particle": ALGO_BYTES[kind], "avg_launch_ms": launch_ms,
+         "share_of_step": launch_ms / max(total_ms, 1e-9)}
+    if work and "candidate_tests_per_pass" in work and sm_mhz:
+        ops = (work["candidate_tests_per_pass"] * LANE_OPS_PER_TEST + work["accepted_pairs_per_pass"] * LANE_OPS_PER_DENSITY_HIT
+               if kind == "density" else work["accepted_pairs_per_pass"] * LANE_OPS_PER_FORCE_PAIR)
+        lane_peak = 148 * 128 * sm_mhz * 1e6
+        e["compute_side"] = {"fp32_lane_ops_per_launch": int(ops), "achieved_lane_ops_per_s": ops / (launch_ms * 1e-3),
+                             "peak_lane_ops_per_s": lane_peak, "frac": ops / (launch_ms * 1e-3) / lane_peak,
+                             "formula": "density: tests x 7 + pairs x 30; force: pairs x 54; peak = 148 SMs x 128 lanes x SM clock"}
+    return e
+
 
 
 class ClockSampler:
@@ -107,22 +151,31 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def best_thread_count(o):
-    """Give the CPU arm its best shot: the pair loops are memory-latency bound and SMT siblings can
-    hurt, so time one step at cpu_count, /2 and /4 threads and keep the fastest."""
+def best_thread_count(o, reps=3):
+    """Give the CPU arm its best shot: the pair loops are memory-latency bound and SMT siblings can hurt, so
+    time `reps` steps (after one untimed step) at cpu_count, /2 and /4 threads and keep the fastest.  Returns
+    (best, {threads: steps/s}) -- round 1 timed ONE step per candidate and picked 32 threads on one box and 64 on
+    another for the same scene (3.5x swing in the reference arm)."""
     from oracle.sph_oracle import set_threads
     total = os.cpu_count() or 1
-    best, best_t = total, float("inf")
+    table = {}
     for n in sorted({total, max(1, total // 2), max(1, total // 4)}, reverse=True):
         set_threads(n)
         o.step()
         t0 = time.perf_counter()
-        o.step()
-        t = time.perf_counter() - t0
-        if t < best_t:
-            best, best_t = n, t
+        for _ in range(reps):
+            o.step()
+        table[n] = reps / (time.perf_counter() - t0)
+    best = max(table, key=table.get)
     set_threads(best)
-    return best
+    return best, table
+
+
+def thread_note(best, table):
+    ranked = sorted(table.items(), key=lambda kv: -kv[1])
+    return (f"OpenMP (OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')}, OMP_PLACES={os.environ.get('OMP_PLACES')}) on {best} of "
+            f"{os.cpu_count()} host threads; candidates timed over 3 steps each: "
+            + ", ".join(f"{n} thr {v:.1f} steps/s" for n, v in ranked))
 
 
 def time_cpu_oracle(scene_dict, budget_s=20.0, max_steps=200):
@@ -130,7 +183,7 @@ def time_cpu_oracle(scene_dict, budget_s=20.0, max_steps=200):
     from oracle.sph_oracle import OracleSim
     o = OracleSim(scene_dict)
     o.initialize()
-    cores = best_thread_count(o)
+    cores, table = best_thread_count(o)
     t0 = time.perf_counter()
     o.step()
     t1 = time.perf_counter() - t0
@@ -140,9 +193,9 @@ def time_cpu_oracle(scene_dict, budget_s=20.0, max_steps=200):
         o.step()
     dt = time.perf_counter() - t0
     return {"value": k / dt * o.n / 1e6, "unit": UNIT, "steps_per_s": k / dt, "cores": cores, "kind": "port",
-            "sample": f"{k} full steps of the same scene ({o.n} particles) after 2 warm-up steps, "
-                      f"OpenMP on {cores} of {os.cpu_count()} host threads (fastest of N, N/2, N/4); restatement of "
-                      "the reference kernels, not Taichi's ti.cpu codegen"}, o.n
+            "threads_tried": {str(n): round(v, 2) for n, v in table.items()},
+            "sample": f"{k} full steps of the same scene ({o.n} particles) after the thread-count probe; "
+                      + thread_note(cores, table) + "; restatement of the reference kernels, not Taichi's ti.cpu codegen"}, o.n
 
 
 def run_reference(args):
@@ -154,7 +207,7 @@ def run_reference(args):
     from oracle.sph_oracle import OracleSim
     o = OracleSim(sc)
     o.initialize()
-    cores = best_thread_count(o)
+    cores, table = best_thread_count(o)
     t0 = time.perf_counter()
     o.step()
     first = time.perf_counter() - t0
@@ -173,10 +226,11 @@ def run_reference(args):
         "n_gpus": args.gpus,
         "steps": k, "warmup": warm, "requested_steps": args.steps, "ms_per_step": 1e3 * dt / k,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "particles": o.n, "solver": "WCSPH", "dt": sc["Configuration"]["timeStepSize"]},
+        "config": workload_config(name, sc, o.n, int((o.material == 1).sum())),
         "cpu_baseline": {"value": val * o.n / 1e6, "unit": UNIT, "steps_per_s": val, "cores": cores, "kind": "port",
-                         "sample": f"{k} full steps of {name} ({o.n} particles) on {cores} of {os.cpu_count()} host threads (OpenMP C "
-                                   "restatement of the reference; Taichi cannot be installed offline)"},
+                         "threads_tried": {str(n_): round(v_, 2) for n_, v_ in table.items()},
+                         "sample": f"{k} full steps of {name} ({o.n} particles); " + thread_note(cores, table)
+                                   + " (OpenMP C restatement of the reference; Taichi cannot be installed offline)"},
         "e2e": {"value": val * o.n / 1e6, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -261,9 +315,7 @@ def run_single(args):
         for k_, v_ in eng.profile_step().items():
             stages[k_] = stages.get(k_, 0.0) + v_ / P
     torch.cuda.synchronize()
-    force_ms = stages.get("force", 0.0)
     peak, peak_src = measured_hbm_peak()
-    achieved = FORCE_BYTES_PER_PARTICLE * n / (force_ms * 1e-3) / 1e9 if force_ms > 0 else 0.0
 
     # ---- e2e: public surface, pinned host buffers, H2D + step + D2H every step ----
     hx = torch.empty((n, 3), dtype=torch.float32).pin_memory()
@@ -304,9 +356,31 @@ def run_single(args):
     except Exception as exc:  # diagnostics only: never lose the bench line over it
         compute = {"error": str(exc)[:200]}
 
+    # ---- BASELINE cfg 3 in the same run (short leg; the driver only ever launches N = 1 with the default scene) ----
+    extra = []
+    if args.scene is None and os.environ.get("SPH_BENCH_SKIP_EXTRA") != "1":
+        try:
+            extra.append(extra_leg("armadillo_bath_dynamic", steps=20, warmup=10))
+        except Exception as exc:  # never lose the main line over the extra leg
+            extra.append({"workload": "armadillo_bath_dynamic", "error": str(exc)[:200]})
+
     cpu, _ = time_cpu_oracle(sc, budget_s=float(os.environ.get("SPH_BENCH_CPU_BUDGET_S", "15")))
 
     val = K / (cold_ms * 1e-3)
+    total_ms = stages.get("total", 0.0)
+    work = compute if compute and "error" not in compute else None
+    kernels = [roofline_entry(kind, name, n, stages.get(kind, 0.0), total_ms, peak, work, clocks.get("sm_mhz"))
+               for kind in ("density", "force") if stages.get(kind, 0.0) > 0]
+    kernels.sort(key=lambda e: -e["avg_launch_ms"])
+    roof = dict(kernels[0]) if kernels else {"bound": "hbm", "achieved": 0.0, "peak": peak, "unit": "GB/s", "frac": 0.0,
+                                             "traffic": None}
+    roof.update(peak_source=peak_src, kernels=kernels,
+                whole_step={"algorithmic_bytes": 368 * n + 12 * int(ps.grid_num.prod()),
+                            "achieved": (368 * n + 12 * int(ps.grid_num.prod())) / (cold_ms / K * 1e-3) / 1e9, "unit": "GB/s"},
+                note="the top-level fields are the DOMINANT kernel of the step (largest CUDA-event time, un-graphed "
+                     "sph_profile_step, 20 steps); `kernels` lists both pair kernels.  They are fp32-issue / L1 bound "
+                     "(~80-100 flop/B), so the HBM fraction is small by construction; `compute_side` is the same launch "
+                     "against the fp32 lane-op peak (DESIGN.md section 5)")
     line = {
         "metric": METRIC, "value": val * n / 1e6, "unit": UNIT, "steps_per_s": val, "n_gpus": 1, "steps": K,
         "warmup": W, "ms_per_step": cold_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -315,31 +389,58 @@ def run_single(args):
                    "ms_per_step": steady_ms / K,
                    "note": "back-to-back CUDA-graph steps, state L2-resident (no flush)"},
         "readme_rtx3090_steps_per_s": 280.0 if name == "dragon_bath" else None,
-        "config": {"workload": name, "particles": n, "fluid_particles": ps.fluid_particle_num,
-                   "grid_cells": int(ps.grid_num.prod()),
-                   "solver": "WCSPH" if sc["Configuration"]["simulationMethod"] == 0 else "DFSPH",
-                   "dt": sc["Configuration"]["timeStepSize"],
-                   "l2": "flushed between timed steps (256 MiB write); 'steady' is un-flushed",
-                   "parallelism": "single GPU"},
+        "config": workload_config(name, sc, n, ps.fluid_particle_num),
         "clocks": clocks,
         "e2e": {"value": Ke / e2e_s * n / 1e6, "unit": UNIT, "steps_per_s": Ke / e2e_s, "steps": Ke,
                 "h2d_bytes_per_step": int(n * 24),
                 "d2h_bytes_per_step": int(n * 24),
                 "pinned_copy_gbs_this_box": round(link_gbs, 2),
-                "note": "ParticleSystem.upload_state -> WCSPHSolver.step -> download_state, pinned host x and v"},
+                "note": "ParticleSystem.upload_state -> WCSPHSolver.step -> download_state, pinned host x and v; "
+                        "link-bound: the two copies alone take 2 x 24 B x particles / the pinned-copy rate"},
         "gpu_launches": int(launches),
         "compute": compute,
-        "roofline": {"kernel": "k_force_packed<4,128,true> (fused cohesion + viscosity + pressure gradient + integration)", "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_force_traffic(name),
-                     "peak_source": peak_src, "algorithmic_bytes_per_particle": FORCE_BYTES_PER_PARTICLE,
-                     "avg_launch_ms": force_ms, "share_of_step": force_ms / max(stages.get("total", 0.0), 1e-9),
-                     "note": "pair kernels are FP32-issue bound (~80-100 flop/B), see DESIGN.md section 5"},
+        "roofline": roof,
         "stage_ms": {k_: round(v_, 5) for k_, v_ in stages.items()},
+        "extra_configs": extra,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     return 0
+
+
+def extra_leg(name, steps, warmup):
+    """A short device-timed leg of another single-GPU BASELINE config (L2 flushed between steps, CUDA events)."""
+    import torch
+    from sph_taichi_b200 import ParticleSystem, SimConfig
+    _, sc = scene_for(1, name)
+    dev = torch.device("cuda:0")
+    ps = ParticleSystem(SimConfig(sc), device=dev)
+    solver = ps.build_solver()
+    solver.initialize()
+    solver.step(warmup)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        solver.step()
+        b.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    ps._engine.check_status()
+    stages = {}
+    for _ in range(5):
+        for k_, v_ in ps._engine.profile_step().items():
+            stages[k_] = stages.get(k_, 0.0) + v_ / 5
+    n = ps.particle_max_num
+    out = {"config": workload_config(name, sc, n, ps.fluid_particle_num), "steps": steps, "warmup": warmup,
+           "ms_per_step": ms, "steps_per_s": 1e3 / ms, "value": 1e3 / ms * n / 1e6, "unit": UNIT,
+           "readme_rtx3090_steps_per_s": 80.0 if name == "armadillo_bath_dynamic" else None,
+           "stage_ms": {k_: round(v_, 5) for k_, v_ in stages.items()}}
+    del solver, ps, flush
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():

@@ -328,6 +328,14 @@ int sph_create(const SphParams *params, int64_t n_max, int64_t n_solid, int32_t 
     if (const char *v = std::getenv("SPH_DENSITY_VARIANT")) c->var_density = std::atoi(v);
     if (const char *v = std::getenv("SPH_FORCE_VARIANT")) c->var_force = std::atoi(v);
     c->P = DevParams{};
+    if (const char *v = std::getenv("SPH_COLUMN_ORDER")) {  // experiments: a permutation of 012345678
+        unsigned long long o = 0ull;
+        unsigned seen = 0u;
+        int k = 0;
+        for (; v[k] >= '0' && v[k] <= '8' && k < 9; ++k) { o |= (unsigned long long)(v[k] - '0') << (4 * k); seen |= 1u << (v[k] - '0'); }
+        if (k == 9 && seen == 0x1ffu && v[9] == 0) c->P.col_order = o;
+        else { delete c; return fail(nullptr, SPH_E_ARG, "SPH_COLUMN_ORDER must be a permutation of 012345678"); }
+    }
     derive_params(c);
     c->P.n = 0;
     c->P.n_solid = 0;

@@ -56,6 +56,7 @@ struct DevParams {
     float fluid_m, fluid_mV;
     int32_t dfsph;  // simulationMethod 4: the density pass neither clamps nor evaluates the EOS
     int32_t opaque_zero;  // always 0; lets a kernel state a scheduling dependency ptxas cannot fold away
+    unsigned long long col_order;  // density v10: nibble p = the (dx, dy) column visited p-th
 };
 
 struct DevArrays {
@@ -254,5 +255,6 @@ inline void derive_dev_params(DevParams &P, const SphParams &h) {
     }
     P.k1_grad = P.k_dw * P.inv_h; P.wd_norm = P.w_diam / P.k2_w;
     P.opaque_zero = 0;
+    if (P.col_order == 0ull) P.col_order = 0x876543210ull;  // raster order (the reference's) unless set before
     P.pad = h.h; P.hi_x = h.clamp_hi[0]; P.hi_y = h.clamp_hi[1]; P.hi_z = h.clamp_hi[2];
 }

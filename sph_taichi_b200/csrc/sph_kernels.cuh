@@ -923,19 +923,16 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
 #ifndef DENS10_MIN_BLOCKS
 #define DENS10_MIN_BLOCKS 8
 #endif
+#ifndef DENS10_SLOTS
+#define DENS10_SLOTS 12  // nine columns + the occasional second chunk of a long column
+#endif
 #ifndef DENS10_PACKED
 #define DENS10_PACKED 0  // 1: FADD2 / FFMA2 on the (x, y) (z, w) halves of a quad
 #endif
-#ifndef DENS10_SYMMETRIC
-#define DENS10_SYMMETRIC 0  // 1: visit the columns as corners, centre, edges (list order only; sums within tolerance)
-#endif
-__device__ __forceinline__ int dens10_column(int p) {
-#if DENS10_SYMMETRIC
-    return (int)((0x753148620ull >> (4 * p)) & 15ull);  // 0, 2, 6, 8, 4, 1, 3, 5, 7
-#else
-    return p;
-#endif
-}
+// Column visiting order (DevParams::col_order, one nibble per position): the list order is free -- only the
+// summation order of the two pair passes depends on it -- and the force pass gathers measurably faster when the
+// nine (dx, dy) columns are not walked in raster order (profiles/r02_column_order.txt).
+__device__ __forceinline__ int dens10_column(const DevParams &P, int p) { return (int)((P.col_order >> (4 * p)) & 15ull); }
 __device__ __forceinline__ float4 ldg_quad(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
 // distance pre-filter of up to 32 candidates jb .. jb + len - 1 (jb a multiple of 4), eight per step:
@@ -980,6 +977,8 @@ __device__ __forceinline__ uint32_t scan_soa(const DevParams &P, const float *__
 
 template <bool FASTW>
 __global__ void __launch_bounds__(DENS10_THREADS, DENS10_MIN_BLOCKS) k_density_soa(DevParams P, DevArrays S) {
+    __shared__ uint32_t s_m[DENS10_SLOTS][DENS10_THREADS];   // per-thread slots: hit masks of the scanned chunks
+    __shared__ int32_t s_top[DENS10_SLOTS][DENS10_THREADS];  // and the candidate index of bit 0
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < P.n && !(P.slab_on && S.grid_ids[min(i, P.n - 1)] >= P.C);
@@ -1035,39 +1034,37 @@ __global__ void __launch_bounds__(DENS10_THREADS, DENS10_MIN_BLOCKS) k_density_s
     float den = 0.0f;
     uint32_t widx = (uint32_t)(fluid ? i : 0);  // index of the next list slot
     const uint32_t widx_cap = widx + (uint32_t)(NBR_CAP - 1) * (uint32_t)S.npad;  // last row
-    auto flush = [&](uint32_t m, int jb, int len) {
-        if ((uint32_t)(i - jb) < (uint32_t)len) m &= ~(1u << (len - 1 - (i - jb)));  // p_i != p_j
-        while (m) {
-            int hb = 31 - __clz(m);  // highest set bit = earliest candidate: keeps the reference order
-            m &= ~(1u << hb);
-            int j = jb + len - 1 - hb;
-            SPH_EMU_CHECK(j >= 0 && j < P.n);
-            float4 pj = __ldg(S.posm + j);
-            float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-            float r2 = exact_r2(rx, ry, rz);
-            if (r2 < P.h2) {  // the exact `norm() < h` of the reference; the scan only pre-filters
-                SPH_EMU_CHECK((uint64_t)widx < (uint64_t)NBR_CAP * (uint64_t)S.npad);
-                S.nbr_list[widx] = j;  // beyond NBR_CAP the last row is overwritten (flagged below)
-                widx = min(widx + (uint32_t)S.npad, widx_cap);
-                ++cnt;
-                if (FASTW) {
-                    den = fmaf(pj.w, spline_w_norm(P, r2), den);
-                } else {
-                    float r, inv_r;
-                    fast_norm(r2, r, inv_r);
-                    den += pj.w * w_cubic(P, r);
-                }
+    // one pre-filtered candidate: the exact `norm() < h` of the reference, list append, density contribution
+    auto visit = [&](int j, const float4 &pj) {
+        SPH_EMU_CHECK(j >= 0 && j < P.n);
+        float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+        float r2 = exact_r2(rx, ry, rz);
+        if (r2 < P.h2) {
+            SPH_EMU_CHECK((uint64_t)widx < (uint64_t)NBR_CAP * (uint64_t)S.npad);
+            S.nbr_list[widx] = j;  // beyond NBR_CAP the last row is overwritten (flagged below)
+            widx = min(widx + (uint32_t)S.npad, widx_cap);
+            ++cnt;
+            if (FASTW) {
+                den = fmaf(pj.w, spline_w_norm(P, r2), den);
+            } else {
+                float r, inv_r;
+                fast_norm(r2, r, inv_r);
+                den += pj.w * w_cubic(P, r);
             }
         }
     };
 
-    int e_next = fast ? col_entry(dens10_column(0)) : 0;
+    // ---- phase 1: scan all nine columns; the hit masks go to this thread's slots in shared memory ----
+    // (slot = {mask, index of the candidate in bit 0}; highest set bit = earliest candidate)
+    const int tid = threadIdx.x;
+    int nch = 0;
+    int e_next = fast ? col_entry(dens10_column(P, 0)) : 0;
     for (int p = 0; p < 9; ++p) {
-        const int c = dens10_column(p);
+        const int c = dens10_column(P, p);
         int j0, j1;
         if (fast) {
             const int e = e_next;
-            if (p + 1 < 9) e_next = col_entry(dens10_column(p + 1));
+            if (p + 1 < 9) e_next = col_entry(dens10_column(P, p + 1));
             j0 = __shfl_sync(0xffffffffu, e, k_lo - kmin + 1);
             j1 = __shfl_sync(0xffffffffu, e, k_hi - kmin + 2);
             if (!fluid || e < 0) { j0 = 0; j1 = 0; }  // e < 0 is warp-uniform (column outside the grid)
@@ -1080,7 +1077,49 @@ __global__ void __launch_bounds__(DENS10_THREADS, DENS10_MIN_BLOCKS) k_density_s
             const int len = min(32, j1 - jb);
             uint32_t m = scan_soa(P, S.sx, S.sy, S.sz, jb, len, pi.x, pi.y, pi.z);
             if (jb < j0) m &= 0xffffffffu >> (32 - len + (j0 - jb));  // candidates jb .. j0 - 1 are the top bits
-            flush(m, jb, len);
+            if ((uint32_t)(i - jb) < (uint32_t)len) m &= ~(1u << (len - 1 - (i - jb)));  // p_i != p_j
+            if (m == 0u) continue;
+            const int top = jb + len - 1;
+            if (nch < DENS10_SLOTS) {
+                s_m[nch][tid] = m;
+                s_top[nch][tid] = top;
+                ++nch;
+            } else {  // more non-empty chunks than slots (very dense state): evaluate this one right away
+                while (m) {
+                    int hb = 31 - __clz(m);
+                    m &= ~(1u << hb);
+                    visit(top - hb, __ldg(S.posm + top - hb));
+                }
+            }
+        }
+    }
+    // ---- phase 2: ONE loop over the hits of all columns (a per-column loop costs the warp the sum over columns
+    // of the per-column maxima: 50 iterations at 18 active lanes; this one the maximum of the per-lane totals),
+    // with the next candidate's position requested before the current one is evaluated ----
+    {
+        int k = 0, top = 0;
+        uint32_t m = 0u;
+        auto next = [&](int &j) -> bool {
+            while (m == 0u) {
+                if (k >= nch) return false;
+                m = s_m[k][tid];
+                top = s_top[k][tid];
+                ++k;
+            }
+            int hb = 31 - __clz(m);
+            m &= ~(1u << hb);
+            j = top - hb;
+            return true;
+        };
+        int j = 0;
+        bool have = next(j);
+        float4 pj = have ? __ldg(S.posm + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        while (have) {
+            int jn = j;
+            const bool hn = next(jn);
+            const float4 pn = __ldg(S.posm + jn);  // (jn == j when the lane has no further hit)
+            visit(j, pj);
+            j = jn; pj = pn; have = hn;
         }
     }
     if (!fluid) return;
