@@ -29,7 +29,7 @@ struct Layout {
     uint64_t off_cid, off_grid_ids, off_perm, off_ticket;
     uint64_t off_zero_begin, off_tile_counter, off_tile_state, off_cell_end, off_zero_end;
     uint64_t off_solid_slot, off_status, off_bodies, off_scratch, off_nbr_list, off_nbr_cnt;
-    uint64_t off_soa[3];
+    uint64_t off_soa[4];
     int64_t npad;
     uint64_t total;
     int n_tiles;
@@ -62,7 +62,7 @@ Layout make_layout(int64_t n_max, int64_t C, int64_t n_solid, int n_bodies) {
     L.npad = (int64_t)align_up(n, 32);
     L.off_nbr_cnt = take((uint64_t)L.npad * 4);
     L.off_nbr_list = take((uint64_t)L.npad * 4 * NBR_CAP);
-    for (int a = 0; a < 3; ++a) L.off_soa[a] = take((uint64_t)(L.npad + 32) * 4);  // +32: the scan reads whole groups of 8
+    for (int a = 0; a < 4; ++a) L.off_soa[a] = take((uint64_t)(L.npad + 32) * 4);  // +32: the scan reads whole groups of 8
     L.total = o;
     return L;
 }
@@ -151,6 +151,7 @@ void bind_arrays(SphCtx *c) {
     S.sx = reinterpret_cast<float *>(w + L.off_soa[0]);
     S.sy = reinterpret_cast<float *>(w + L.off_soa[1]);
     S.sz = reinterpret_cast<float *>(w + L.off_soa[2]);
+    S.sw = reinterpret_cast<float *>(w + L.off_soa[3]);
 }
 
 inline RigidBodyDev *dev_bodies(SphCtx *c) { return reinterpret_cast<RigidBodyDev *>(c->ws + c->L.off_bodies); }

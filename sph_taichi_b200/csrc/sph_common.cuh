@@ -84,9 +84,10 @@ struct DevArrays {
     int32_t *nbr_list;
     int32_t *nbr_cnt;
     int32_t npad;
-    // SoA copy of the sorted positions (written by k_rank_move, valid while `built`): the density scan reads
-    // FOUR consecutive candidates per 128-bit load from each row (rows are padded by 32 floats)
-    float *sx, *sy, *sz;
+    // SoA copy of posm = {x, y, z, m_V} (written by k_rank_move, m_V patched by k_boundary_volume; valid while
+    // `built`): the density scan reads FOUR consecutive candidates per 128-bit load from each row (rows are
+    // padded by 32 floats)
+    float *sx, *sy, *sz, *sw;  // x, y, z, m_V
 };
 
 constexpr int NBR_CAP = 96;  // soak runs of the shipped scenes peak at 54 neighbours (tools/soak.py)

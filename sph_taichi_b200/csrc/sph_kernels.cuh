@@ -264,7 +264,7 @@ __global__ void k_rank_move(DevParams P, DevArrays S) {
     float4 misc = S.misc[src];
     const float4 pm = S.posm[src];
     S.posm_n[dst] = pm;
-    S.sx[dst] = pm.x; S.sy[dst] = pm.y; S.sz[dst] = pm.z;
+    S.sx[dst] = pm.x; S.sy[dst] = pm.y; S.sz[dst] = pm.z; S.sw[dst] = pm.w;
     S.veld_n[dst] = S.veld[src];
     S.x0id_n[dst] = S.x0id[src];
     S.misc_n[dst] = misc;
@@ -319,7 +319,11 @@ __global__ void __launch_bounds__(128) k_boundary_volume(DevParams P, DevArrays 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     // only .w changes; concurrent readers use .xyz only
-    if (lane == 0) reinterpret_cast<float *>(S.posm + i)[3] = 1.0f / (P.w0 + part) * 3.0f;
+    if (lane == 0) {
+        const float mv = 1.0f / (P.w0 + part) * 3.0f;
+        reinterpret_cast<float *>(S.posm + i)[3] = mv;
+        S.sw[i] = mv;  // the SoA copy the density scan reads
+    }
 }
 
 // Densities (WCSPH.py:33-43).  FUSE_EOS additionally applies the clamp + Tait EOS of
@@ -1055,21 +1059,41 @@ __global__ void __launch_bounds__(DENS10_THREADS, DENS10_MIN_BLOCKS) k_density_s
     };
 
     // ---- phase 1: scan all nine columns; the hit masks go to this thread's slots in shared memory ----
-    // (slot = {mask, index of the candidate in bit 0}; highest set bit = earliest candidate)
+    // (slot = {mask, index of the candidate in bit 0}; highest set bit = earliest candidate).
+    // Software pipeline over the columns (fast path): while column p is scanned, the rows of column p + 1 are
+    // already requested (prefetch.global.L1: the first touch of a window comes from L2) and the cell_end
+    // entries of column p + 2 are in flight.
     const int tid = threadIdx.x;
     int nch = 0;
-    int e_next = fast ? col_entry(dens10_column(P, 0)) : 0;
+    auto fast_range = [&](int e, int &j0, int &j1) {
+        j0 = __shfl_sync(0xffffffffu, e, k_lo - kmin + 1);
+        j1 = __shfl_sync(0xffffffffu, e, k_hi - kmin + 2);
+        if (!fluid || e < 0) { j0 = 0; j1 = 0; }  // e < 0 is warp-uniform (column outside the grid)
+    };
+    auto prefetch_rows = [&](int j0, int j1) {
+        if (j1 > j0) {
+            const int a = j0 & ~3;
+            prefetch_l1(S.sx + a); prefetch_l1(S.sy + a); prefetch_l1(S.sz + a); prefetch_l1(S.sw + a);
+            prefetch_l1(S.sx + j1 - 1); prefetch_l1(S.sy + j1 - 1); prefetch_l1(S.sz + j1 - 1); prefetch_l1(S.sw + j1 - 1);
+        }
+    };
+    int j0n = 0, j1n = 0, e_next = 0;
+    if (fast) {
+        fast_range(col_entry(dens10_column(P, 0)), j0n, j1n);
+        prefetch_rows(j0n, j1n);
+        e_next = col_entry(dens10_column(P, 1));
+    }
     for (int p = 0; p < 9; ++p) {
-        const int c = dens10_column(P, p);
         int j0, j1;
         if (fast) {
-            const int e = e_next;
-            if (p + 1 < 9) e_next = col_entry(dens10_column(P, p + 1));
-            j0 = __shfl_sync(0xffffffffu, e, k_lo - kmin + 1);
-            j1 = __shfl_sync(0xffffffffu, e, k_hi - kmin + 2);
-            if (!fluid || e < 0) { j0 = 0; j1 = 0; }  // e < 0 is warp-uniform (column outside the grid)
+            j0 = j0n; j1 = j1n;
+            if (p + 1 < 9) {
+                fast_range(e_next, j0n, j1n);
+                prefetch_rows(j0n, j1n);
+                if (p + 2 < 9) e_next = col_entry(dens10_column(P, p + 2));
+            }
         } else {
-            col_range_slow(c, j0, j1);
+            col_range_slow(dens10_column(P, p), j0, j1);
         }
         if (j1 <= j0) continue;
         const int a0 = j0 & ~3;  // quads are 16-byte aligned: up to 3 candidates below the range are scanned and dropped
@@ -1088,36 +1112,34 @@ __global__ void __launch_bounds__(DENS10_THREADS, DENS10_MIN_BLOCKS) k_density_s
                 while (m) {
                     int hb = 31 - __clz(m);
                     m &= ~(1u << hb);
-                    visit(top - hb, __ldg(S.posm + top - hb));
+                    const int j = top - hb;
+                    visit(j, make_float4(__ldg(S.sx + j), __ldg(S.sy + j), __ldg(S.sz + j), __ldg(S.sw + j)));
                 }
             }
         }
     }
     // ---- phase 2: ONE loop over the hits of all columns (a per-column loop costs the warp the sum over columns
-    // of the per-column maxima: 50 iterations at 18 active lanes; this one the maximum of the per-lane totals),
-    // with the next candidate's position requested before the current one is evaluated ----
+    // of the per-column maxima: 50 iterations at 18 active lanes; this one the maximum of the per-lane totals: 30
+    // at 30), reading the candidate from the SoA rows the scan has just pulled into L1, one candidate ahead ----
     {
         int k = 0, top = 0;
         uint32_t m = 0u;
+        // every stored mask is non-empty, so ONE predicated refill keeps the loop free of inner branches
         auto next = [&](int &j) -> bool {
-            while (m == 0u) {
-                if (k >= nch) return false;
-                m = s_m[k][tid];
-                top = s_top[k][tid];
-                ++k;
-            }
-            int hb = 31 - __clz(m);
+            if (m == 0u && k < nch) { m = s_m[k][tid]; top = s_top[k][tid]; ++k; }
+            const bool ok = m != 0u;
+            const int hb = 31 - __clz(m | 1u);
             m &= ~(1u << hb);
-            j = top - hb;
-            return true;
+            j = ok ? top - hb : j;
+            return ok;
         };
-        int j = 0;
+        int j = min(i, P.n - 1);
         bool have = next(j);
-        float4 pj = have ? __ldg(S.posm + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 pj = make_float4(__ldg(S.sx + j), __ldg(S.sy + j), __ldg(S.sz + j), __ldg(S.sw + j));
         while (have) {
             int jn = j;
-            const bool hn = next(jn);
-            const float4 pn = __ldg(S.posm + jn);  // (jn == j when the lane has no further hit)
+            const bool hn = next(jn);  // jn == j when the lane has no further hit
+            const float4 pn = make_float4(__ldg(S.sx + jn), __ldg(S.sy + jn), __ldg(S.sz + jn), __ldg(S.sw + jn));
             visit(j, pj);
             j = jn; pj = pn; have = hn;
         }
@@ -1252,6 +1274,9 @@ __device__ __forceinline__ void force_pair_packed(const DevParams &P, const DevA
 #ifndef FORCE_THREADS
 #define FORCE_THREADS 128
 #endif
+#ifndef FORCE_PREFETCH
+#define FORCE_PREFETCH 1
+#endif
 // split_info / split_mode (slab mode): process only the particles inside (mode 0) or outside (mode 1)
 // the index ranges this rank sends to its neighbours (info[1..8) / info[9..4), see k_slab_info), so
 // that the halo exchange of the next step can start while the interior is still being computed.
@@ -1284,11 +1309,41 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
         // 32-bit list slots (sph_create bounds NBR_CAP * npad below 2^32): one IADD + one IMAD.WIDE per load
         const uint32_t np = (uint32_t)S.npad;
         uint32_t slot = (uint32_t)i;
+#if FORCE_PREFETCH
+        // Two-deep software pipeline WITHOUT holding records in registers: while batch t is evaluated, the indices
+        // of batch t + 1 are already loaded and its records requested into L1 (CCTL.E.PF1), and the list rows of
+        // batch t + 2 are requested too -- the gathers of a batch then hit L1 instead of waiting ~300 cycles
+        // behind a dependent list load (v8 profile: 10 warps per issue stalled on long_scoreboard).
+        int jn[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) jn[u] = (cnt > 0) ? __ldg(S.nbr_list + (slot + (uint32_t)u * np)) : i;
+#pragma unroll
+        for (int u = 0; u < B; ++u) prefetch_l1(S.fpv + 2 * (size_t)jn[u]);
+        if (cnt > B) {
+#pragma unroll
+            for (int u = 0; u < B; ++u) prefetch_l1(S.nbr_list + (slot + (uint32_t)(B + u) * np));
+        }
+#endif
         for (int k0 = 0; k0 < cnt; k0 += B) {
             int j[B];  // the density pass padded the list to a multiple of LIST_PAD with i itself
             float4 pj[B], vj[B];
+#if FORCE_PREFETCH
+#pragma unroll
+            for (int u = 0; u < B; ++u) j[u] = jn[u];
+            if (k0 + B < cnt) {
+#pragma unroll
+                for (int u = 0; u < B; ++u) jn[u] = __ldg(S.nbr_list + (slot + (uint32_t)(B + u) * np));
+#pragma unroll
+                for (int u = 0; u < B; ++u) prefetch_l1(S.fpv + 2 * (size_t)jn[u]);
+                if (k0 + 2 * B < cnt) {
+#pragma unroll
+                    for (int u = 0; u < B; ++u) prefetch_l1(S.nbr_list + (slot + (uint32_t)(2 * B + u) * np));
+                }
+            }
+#else
 #pragma unroll
             for (int u = 0; u < B; ++u) j[u] = ldg_stream(S.nbr_list + (slot + (uint32_t)u * np));
+#endif
 #pragma unroll
             for (int u = 0; u < B; ++u) SPH_EMU_CHECK(k0 + u < NBR_CAP && j[u] >= 0 && j[u] < P.n);  // padded with i
 #pragma unroll
