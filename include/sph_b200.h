@@ -41,6 +41,8 @@ extern "C" {
 /* device status word bits (sph_read_status) */
 #define SPH_STATUS_OUT_OF_GRID 1u /* a particle hashed outside the grid (reference: OOB write) */
 #define SPH_STATUS_BAD_POLAR 2u   /* shape matching hit a singular A */
+#define SPH_STATUS_HALO_CAPACITY 4u  /* sharded: a send range exceeded halo_capacity (records were cut off) */
+#define SPH_STATUS_SHARD_CAPACITY 8u /* sharded: live + received records ran into the receive regions */
 
 /* Scalar parameters.  All constants are folded in double on the host exactly as the
  * reference folds them in Python scope before Taichi bakes them into kernels
@@ -92,7 +94,7 @@ typedef struct SphCtx SphCtx;
 /* ---- lifetime ------------------------------------------------------------------------ */
 /* Workspace bytes needed for n_max particles, n_solid solid particles, n_bodies bodies.
  * Capacity: 96 * round_up(n_max, 32) < 2^32 (per-step neighbour lists use 32-bit slots), i.e. n_max <= 44.7 M
- * particles per GPU; sph_create returns SPH_E_CAPACITY beyond that (shard by x-slabs, sph_slab_*). */
+ * particles per GPU; sph_create returns SPH_E_CAPACITY beyond that (shard by x-slabs, sph_shard_*). */
 uint64_t sph_workspace_bytes(const SphParams *params, int64_t n_max, int64_t n_solid, int32_t n_bodies);
 int sph_create(const SphParams *params, int64_t n_max, int64_t n_solid, int32_t n_bodies, int32_t device,
                void *workspace, uint64_t workspace_bytes, SphCtx **out);
@@ -162,27 +164,53 @@ int sph_set_dfsph(SphCtx *ctx, int32_t enable);
 int sph_dfsph_op(SphCtx *ctx, int32_t op, float arg, void *out_dev, void *stream);
 
 /* ---- x-slab sharding across the GPUs of one node (new; the reference is single-device) -------
- * One process per GPU.  Each rank owns the cell layers [x_lo, x_hi) of the x axis and keeps
- * `ghost_layers` (2) layers of copies of its neighbours' particles, so one exchange per step
- * suffices: the caller (sph_taichi_b200/slab.py) sends the raw records of its boundary layers
- * with NCCL straight out of / into the packed arrays (sph_state_offsets), appends what it
- * received behind the local records (sph_slab_set_counts) and calls sph_slab_step, which
- * classifies every record as owned / ghost / dropped from its position alone, sorts, reports
- * the next send ranges in info_dev[12] = {live, sendL_begin, sendL_end, sendR_begin, sendR_end,
- * processed, owned, status, sendL_end_wide, sendR_begin_wide, x_lo, x_hi} and advances the owned
- * particles.  Calling sph_slab_configure again between steps moves the slab by at most one layer per
- * side (load re-balancing); on such a step the neighbours exchange the *_wide ranges. */
-int sph_slab_configure(SphCtx *ctx, int32_t x_lo, int32_t x_hi, int32_t ghost_layers);
-int sph_slab_set_counts(SphCtx *ctx, int64_t n_local, int64_t n_recv);
+ * One process per GPU.  Each rank owns the cell layers [x_lo, x_hi) of the x axis (x-major flattening,
+ * particle_system.py:292-294: after the sort every layer is ONE contiguous index range) and keeps
+ * `ghost_layers` (2) layers of copies of its neighbours' particles, so ONE exchange per step suffices.
+ * Everything a step needs lives on the device -- live count, slab bounds, send / receive ranges, record counts
+ * (carried in-band in a header) -- so a whole sharded step replays from one CUDA graph:
+ *
+ *     plan (receive counts, cut re-balancing) -> classify + sort -> info (send ranges) -> density ->
+ *     forces + integration of the boundary particles -> pack -> { halo exchange of the NEXT step  ||
+ *     forces + integration of the interior }
+ *
+ * and the host only launches graphs.  Every record is classified as owned / ghost / dropped from its position
+ * alone (both ranks evaluate the same fp32 expression), so migration needs no extra message; cuts move by at
+ * most one layer every `rebalance_every` steps, decided identically on both sides of a cut from the owned
+ * counts in the headers.  Fluid-only scenes with one fluid (uniform masses); rigid bodies are single-GPU.
+ *
+ * The exchange goes through an SphTransport: NCCL point-to-point (libnccl.so.2 is dlopen'ed; the communicator
+ * belongs to this library, created from an id the caller distributes), or caller-supplied functions (the CPU
+ * test-suite routes them to torch.distributed / gloo against the host-emulated build). */
+typedef struct SphTransport {
+    void *user;
+    int (*group_start)(void *user);
+    int (*group_end)(void *user, void *stream);
+    int (*send)(void *user, const void *buf, uint64_t bytes, int32_t peer, void *stream);
+    int (*recv)(void *user, void *buf, uint64_t bytes, int32_t peer, void *stream);
+} SphTransport;
+int sph_comm_unique_id(char out128[128]);                                  /* ncclGetUniqueId (rank 0) */
+int sph_comm_init_nccl(SphCtx *ctx, const char id128[128], int32_t rank, int32_t world); /* ncclCommInitRank */
+int sph_comm_set_transport(SphCtx *ctx, const SphTransport *t, int32_t rank, int32_t world);
+/* The context must have been created with n_max = the per-rank CAPACITY (owned + ghosts + trash + 2 *
+ * halo_capacity receive slots) and packed with this rank's initial particles.  halo_capacity = records per
+ * side and direction (>= (ghost_layers + 2) fullest layers). */
+int sph_shard_configure(SphCtx *ctx, int32_t x_lo, int32_t x_hi, int32_t ghost_layers, int64_t halo_capacity,
+                        int32_t rebalance_every);
+/* first sort of the packed particles + the first halo exchange (no physics) */
+int sph_shard_begin(SphCtx *ctx, void *stream);
+/* nsteps sharded SPHBase.step()s (sph_base.py:263-271), one CUDA-graph replay per step */
+int sph_shard_step(SphCtx *ctx, int32_t nsteps, void *stream);
+/* the exchange alone: sends the packed staging, receives behind the live records */
+int sph_halo_exchange(SphCtx *ctx, void *stream);
+/* synchronising read of the device-resident step state: out16 = {n_live, owned, x_lo, x_hi, step, own_begin,
+ * own_end, sendL_begin, sendL_end, sendR_begin, sendR_end, recv_left, recv_right, n_sorted, status,
+ * 0}; out_sent (may be NULL) = halo records sent so far */
+int sph_shard_info(SphCtx *ctx, int32_t *out16, uint64_t *out_sent, void *stream);
+/* ONE un-graphed sharded step with CUDA events between its stages; ms_out4 = {sort + bookkeeping, density,
+ * boundary forces + pack, max(interior forces, halo exchange)}; synchronises */
+int sph_shard_profile_step(SphCtx *ctx, float *ms_out4, void *stream);
 int sph_state_offsets(SphCtx *ctx, uint64_t *out5); /* byte offsets of posm, veld, x0id, misc, acc in the workspace */
-int sph_slab_step(SphCtx *ctx, int32_t *info_dev, int32_t sort_only, void *stream);
-int sph_slab_compute(SphCtx *ctx, void *stream); /* the part of sph_slab_step after the sort */
-/* the same in two launches: phase 0 = density + the particles of this rank's send ranges, phase 1 = the
- * rest; the caller posts the next halo exchange in between so that it overlaps the interior work */
-int sph_slab_compute_split(SphCtx *ctx, const int32_t *info_dev, int32_t phase, void *stream);
-/* CUDA-event timing of the density and force launches of sph_slab_compute: enable != 0 switches it on;
- * ms_out (may be NULL) receives {density_ms, force_ms} of the last timed call (synchronises). */
-int sph_slab_pair_times(SphCtx *ctx, int32_t enable, float *ms_out);
 
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 int sph_read_status(SphCtx *ctx, uint32_t *status_out, void *stream); /* synchronises `stream` */

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("SPH_B200_LIB") or os.path.join(_PKG, "libsph_b200.so"
 CSRC = os.path.join(_PKG, "csrc")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "-ldl"]
 
 # every symbol include/sph_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
@@ -24,8 +24,9 @@ ABI_SYMBOLS = [
     "sph_boundary_volume", "sph_compute_densities", "sph_compute_non_pressure_forces", "sph_compute_pressure_forces",
     "sph_advect", "sph_enforce_boundary", "sph_set_rigid_bodies", "sph_compute_com", "sph_compute_rigid_rest_cm",
     "sph_solve_constraints", "sph_get_rigid_state", "sph_step", "sph_read_status", "sph_clear_status", "sph_neighbor_stats", "sph_particle_count",
-    "sph_launch_count", "sph_profile_step", "sph_timer_name", "sph_slab_configure", "sph_slab_set_counts",
-    "sph_state_offsets", "sph_slab_step", "sph_slab_compute", "sph_slab_compute_split", "sph_slab_pair_times", "sph_set_dfsph", "sph_dfsph_op",
+    "sph_launch_count", "sph_profile_step", "sph_timer_name", "sph_state_offsets", "sph_set_dfsph", "sph_dfsph_op",
+    "sph_comm_unique_id", "sph_comm_init_nccl", "sph_comm_set_transport", "sph_shard_configure", "sph_shard_begin",
+    "sph_shard_step", "sph_halo_exchange", "sph_shard_info", "sph_shard_profile_step",
 ]
 
 
@@ -62,6 +63,18 @@ class SphFields(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in (
         "object_id", "x", "x_0", "v", "acceleration", "m_V", "m", "density", "pressure", "material", "is_dynamic",
         "color", "grid_ids", "solid_id", "dfsph_factor", "density_adv")]
+
+
+# halo-exchange transport (include/sph_b200.h: SphTransport); the CPU test-suite fills it with gloo callbacks
+TRANSPORT_GROUP_START = C.CFUNCTYPE(C.c_int, C.c_void_p)
+TRANSPORT_GROUP_END = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+TRANSPORT_SEND = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p)
+TRANSPORT_RECV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p)
+
+
+class SphTransport(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("group_start", TRANSPORT_GROUP_START), ("group_end", TRANSPORT_GROUP_END),
+                ("send", TRANSPORT_SEND), ("recv", TRANSPORT_RECV)]
 
 
 class SphRigidBody(C.Structure):
@@ -121,15 +134,18 @@ def load():
         "sph_launch_count": (i64, [vp]),
         "sph_profile_step": (C.c_int, [vp, C.POINTER(C.c_float), i32, vp]),
         "sph_timer_name": (C.c_char_p, [i32]),
-        "sph_slab_configure": (C.c_int, [vp, i32, i32, i32]),
-        "sph_slab_set_counts": (C.c_int, [vp, i64, i64]),
         "sph_state_offsets": (C.c_int, [vp, C.POINTER(u64)]),
-        "sph_slab_step": (C.c_int, [vp, vp, i32, vp]),
-        "sph_slab_compute": (C.c_int, [vp, vp]),
-        "sph_slab_compute_split": (C.c_int, [vp, vp, i32, vp]),
         "sph_set_dfsph": (C.c_int, [vp, i32]),
         "sph_dfsph_op": (C.c_int, [vp, i32, C.c_float, vp, vp]),
-        "sph_slab_pair_times": (C.c_int, [vp, i32, C.POINTER(C.c_float)]),
+        "sph_comm_unique_id": (C.c_int, [C.c_char_p]),
+        "sph_comm_init_nccl": (C.c_int, [vp, C.c_char_p, i32, i32]),
+        "sph_comm_set_transport": (C.c_int, [vp, C.POINTER(SphTransport), i32, i32]),
+        "sph_shard_configure": (C.c_int, [vp, i32, i32, i32, i64, i32]),
+        "sph_shard_begin": (C.c_int, [vp, vp]),
+        "sph_shard_step": (C.c_int, [vp, i32, vp]),
+        "sph_halo_exchange": (C.c_int, [vp, vp]),
+        "sph_shard_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(u64), vp]),
+        "sph_shard_profile_step": (C.c_int, [vp, C.POINTER(C.c_float), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -1,6 +1,9 @@
 // sph_b200.cu -- host side of libsph_b200.so: context, workspace carving, launch sequences,
 // CUDA-graph step replay, and the extern "C" ABI declared in include/sph_b200.h.
 #include <cuda_runtime.h>
+#ifndef SPH_EMU
+#include <dlfcn.h>
+#endif
 
 #include <cmath>
 #include <cstdio>
@@ -29,7 +32,6 @@ struct Layout {
     uint64_t off_cid, off_grid_ids, off_perm, off_ticket;
     uint64_t off_zero_begin, off_tile_counter, off_tile_state, off_cell_end, off_zero_end;
     uint64_t off_solid_slot, off_status, off_bodies, off_scratch, off_nbr_list, off_nbr_cnt;
-    uint64_t off_soa[4];
     int64_t npad;
     uint64_t total;
     int n_tiles;
@@ -62,10 +64,49 @@ Layout make_layout(int64_t n_max, int64_t C, int64_t n_solid, int n_bodies) {
     L.npad = (int64_t)align_up(n, 32);
     L.off_nbr_cnt = take((uint64_t)L.npad * 4);
     L.off_nbr_list = take((uint64_t)L.npad * 4 * NBR_CAP);
-    for (int a = 0; a < 4; ++a) L.off_soa[a] = take((uint64_t)(L.npad + 32) * 4);  // +32: the scan reads whole groups of 8
     L.total = o;
     return L;
 }
+
+#ifndef SPH_EMU
+// NCCL point-to-point through dlopen: the library has no link-time dependency on NCCL (the CPU test-suite and
+// single-GPU users never load it); inside a PyTorch process the already loaded libnccl.so.2 is reused.
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string err;
+};
+NcclApi g_nccl;
+bool load_nccl() {
+    if (g_nccl.lib) return true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { g_nccl.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+    auto sym = [&](const char *n) { void *p = dlsym(h, n); if (!p) g_nccl.err = std::string("libnccl lacks ") + n; return p; };
+    g_nccl.GetUniqueId = reinterpret_cast<int (*)(NcclId *)>(sym("ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<int (*)(void **, int, NcclId, int)>(sym("ncclCommInitRank"));
+    g_nccl.CommDestroy = reinterpret_cast<int (*)(void *)>(sym("ncclCommDestroy"));
+    g_nccl.GroupStart = reinterpret_cast<int (*)()>(sym("ncclGroupStart"));
+    g_nccl.GroupEnd = reinterpret_cast<int (*)()>(sym("ncclGroupEnd"));
+    g_nccl.Send = reinterpret_cast<int (*)(const void *, size_t, int, int, void *, cudaStream_t)>(sym("ncclSend"));
+    g_nccl.Recv = reinterpret_cast<int (*)(void *, size_t, int, int, void *, cudaStream_t)>(sym("ncclRecv"));
+    g_nccl.GetErrorString = reinterpret_cast<const char *(*)(int)>(sym("ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.GroupStart || !g_nccl.GroupEnd ||
+        !g_nccl.Send || !g_nccl.Recv || !g_nccl.GetErrorString)
+        return false;
+    g_nccl.lib = h;
+    return true;
+}
+#endif
 
 }  // namespace
 
@@ -94,6 +135,17 @@ struct SphCtx {
     cudaStream_t capture_stream = nullptr;  // graphs are captured here (the legacy stream cannot capture)
     bool built = false;  // neighbour structure valid for current positions
     bool list_valid = false;  // neighbour lists valid for current positions (DFSPH kernels)
+    // x-slab sharding (sph_shard_*)
+    SphTransport transport{};
+    bool has_transport = false;
+    int rank = 0, world = 1;
+    void *nccl_comm = nullptr;
+    char *shard_buf = nullptr;  // library-owned: device step state + send staging (cudaMalloc at sph_shard_configure)
+    bool shard_begun = false;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_packed = nullptr, ev_exchanged = nullptr;
+    cudaGraphExec_t graph_shard[2] = {nullptr, nullptr};
+    int64_t graph_shard_kernels[2] = {0, 0};
 };
 
 namespace {
@@ -148,10 +200,14 @@ void bind_arrays(SphCtx *c) {
     S.nbr_list = reinterpret_cast<int32_t *>(w + L.off_nbr_list);
     S.nbr_cnt = reinterpret_cast<int32_t *>(w + L.off_nbr_cnt);
     S.npad = (int32_t)L.npad;
-    S.sx = reinterpret_cast<float *>(w + L.off_soa[0]);
-    S.sy = reinterpret_cast<float *>(w + L.off_soa[1]);
-    S.sz = reinterpret_cast<float *>(w + L.off_soa[2]);
-    S.sw = reinterpret_cast<float *>(w + L.off_soa[3]);
+    S.sd = nullptr;
+    if (c->shard_buf) {  // {state ints | header x 2 | 2 sides x 4 arrays x halo_cap records}
+        S.sd = reinterpret_cast<int32_t *>(c->shard_buf);
+        char *q = c->shard_buf + 256;
+        for (int side = 0; side < 2; ++side) { S.stage_hdr[side] = reinterpret_cast<int32_t *>(q); q += 256; }
+        for (int side = 0; side < 2; ++side)
+            for (int k = 0; k < 4; ++k) { S.stage[side][k] = reinterpret_cast<float4 *>(q); q += align_up((uint64_t)c->P.halo_cap * 16, 256); }
+    }
 }
 
 inline RigidBodyDev *dev_bodies(SphCtx *c) { return reinterpret_cast<RigidBodyDev *>(c->ws + c->L.off_bodies); }
@@ -162,6 +218,7 @@ void drop_graphs(SphCtx *c) {
     for (int k = 0; k < 2; ++k) {
         if (c->graph[k]) { cudaGraphExecDestroy(c->graph[k]); c->graph[k] = nullptr; }
         if (c->graph_multi[k]) { cudaGraphExecDestroy(c->graph_multi[k]); c->graph_multi[k] = nullptr; }
+        if (c->graph_shard[k]) { cudaGraphExecDestroy(c->graph_shard[k]); c->graph_shard[k] = nullptr; }
     }
 }
 
@@ -210,22 +267,16 @@ int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *k
 void launch_pair_density(SphCtx *c, cudaStream_t st, int64_t *kernels) {
     const DevParams &P = c->P;
     const int blocks = blocks_for(P.n, DENS_WARPS * 32);
-    if (c->var_density == 10) {  // v10: SoA quads, no staging
-        const int b10 = blocks_for(P.n, DENS10_THREADS);
-        if (P.dfsph) k_density_soa<false><<<b10, DENS10_THREADS, 0, st>>>(P, c->S);
-        else k_density_soa<true><<<b10, DENS10_THREADS, 0, st>>>(P, c->S);
-    }
-    else if (c->var_density == 0) k_density_tma<false, false><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
+    if (c->var_density == 0) k_density_tma<false, false><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
     else if (P.dfsph || c->var_density == 2) k_density_tma<true, false><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
     else k_density_tma<true, true><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
     *kernels += 1;
 }
-void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels,
-                                  const int32_t *split_info = nullptr, int split_mode = 0) {
+void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels, int split_mode = 0) {
     const DevParams &P = c->P;
     if (P.uniform_fluid && c->var_force != 0) {
         k_force_packed<FORCE_BATCH, FORCE_THREADS, true><<<blocks_for(P.n, FORCE_THREADS), FORCE_THREADS, 0, st>>>(
-            P, c->S, split_info, split_mode);
+            P, c->S, split_mode);
         *kernels += 1;
         if (tm) tm->mark(T_ADVECT);
         if (c->has_dynamic_solids && P.n_solid > 0) {
@@ -234,7 +285,7 @@ void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, in
         }
         return;
     }
-    if (P.uniform_fluid) k_force_packed<FORCE_BATCH, FORCE_THREADS, false><<<blocks_for(P.n, FORCE_THREADS), FORCE_THREADS, 0, st>>>(P, c->S, nullptr, 0);
+    if (P.uniform_fluid) k_force_packed<FORCE_BATCH, FORCE_THREADS, false><<<blocks_for(P.n, FORCE_THREADS), FORCE_THREADS, 0, st>>>(P, c->S, 0);
     else k_force_general<4, 128><<<blocks_for(P.n, 128), 128, 0, st>>>(P, c->S);
     if (tm) tm->mark(T_ADVECT);
     k_advect<true><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
@@ -351,6 +402,13 @@ int sph_destroy(SphCtx *ctx) {
     if (!ctx) return SPH_OK;
     drop_graphs(ctx);
     if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
+#ifndef SPH_EMU
+    if (ctx->nccl_comm && g_nccl.lib) g_nccl.CommDestroy(ctx->nccl_comm);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
+    if (ctx->ev_exchanged) cudaEventDestroy(ctx->ev_exchanged);
+#endif
+    if (ctx->shard_buf) cudaFree(ctx->shard_buf);
     delete ctx;
     return SPH_OK;
 }
@@ -600,26 +658,6 @@ int sph_step(SphCtx *ctx, int32_t nsteps, void *stream) {
     return SPH_OK;
 }
 
-int sph_slab_configure(SphCtx *ctx, int32_t x_lo, int32_t x_hi, int32_t ghost_layers) {
-    if (!ctx) return SPH_E_ARG;
-    if (x_lo < 0 || x_hi > ctx->P.gx || ghost_layers < 1 || x_hi - x_lo < ghost_layers + 1)
-        return fail(ctx, SPH_E_ARG, "slab must lie inside the grid and be at least ghost_layers + 1 cell layers wide");
-    if (!ctx->bodies.empty() || ctx->P.n_solid > 0)
-        return fail(ctx, SPH_E_ARG, "x-slab sharding supports fluid-only scenes (rigid bodies are single-GPU, SURVEY 8e)");
-    ctx->P.slab_on = 1; ctx->P.sx0 = x_lo; ctx->P.sx1 = x_hi; ctx->P.sgw = ghost_layers;
-    ctx->P.n_local = ctx->P.n;
-    drop_graphs(ctx);
-    return SPH_OK;
-}
-
-int sph_slab_set_counts(SphCtx *ctx, int64_t n_local, int64_t n_recv) {
-    if (!ctx || !ctx->P.slab_on || n_local < 0 || n_recv < 0) return SPH_E_ARG;
-    if (n_local + n_recv > ctx->n_max) return fail(ctx, SPH_E_CAPACITY, "slab: local + received particles exceed n_max");
-    ctx->P.n_local = (int32_t)n_local;
-    ctx->P.n = (int32_t)(n_local + n_recv);
-    return SPH_OK;
-}
-
 int sph_state_offsets(SphCtx *ctx, uint64_t *out5) {
     if (!ctx || !out5) return SPH_E_ARG;
     const float4 *cur[5] = {ctx->S.posm, ctx->S.veld, ctx->S.x0id, ctx->S.misc, ctx->S.acc};
@@ -627,84 +665,280 @@ int sph_state_offsets(SphCtx *ctx, uint64_t *out5) {
     return SPH_OK;
 }
 
-int sph_slab_compute(SphCtx *ctx, void *stream);
+// =========================================================================================
+// x-slab sharding (see include/sph_b200.h)
+// =========================================================================================
+}  // extern "C"
+namespace {
 
-// One sharded step: classify + sort (received records are already in place behind the local
-// ones), write the next send ranges to info_dev[8], then density / forces / integration of the
-// owned particles.  sort_only = 1 stops after the sort (initialisation).
-int sph_slab_step(SphCtx *ctx, int32_t *info_dev, int32_t sort_only, void *stream) {
-    if (!ctx || !info_dev) return SPH_E_ARG;
-    if (!ctx->P.slab_on) return fail(ctx, SPH_E_ARG, "sph_slab_configure was not called");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const DevParams &P = ctx->P;
-    if (P.n == 0) { CUDA_TRY(ctx, cudaMemsetAsync(info_dev, 0, 48, st)); return SPH_OK; }
-    int rc = launch_neighbor_build(ctx, st, nullptr, &ctx->launches, /*move_acc=*/false);
+#ifndef SPH_EMU
+// SphTransport over the context's NCCL communicator (user = the SphCtx); ncclInt8 = 0
+int nccl_group_start(void *) { return g_nccl.GroupStart(); }
+int nccl_group_end(void *, void *) { return g_nccl.GroupEnd(); }
+int nccl_send(void *user, const void *buf, uint64_t bytes, int32_t peer, void *stream) {
+    return g_nccl.Send(buf, (size_t)bytes, 0, peer, static_cast<SphCtx *>(user)->nccl_comm, static_cast<cudaStream_t>(stream));
+}
+int nccl_recv(void *user, void *buf, uint64_t bytes, int32_t peer, void *stream) {
+    return g_nccl.Recv(buf, (size_t)bytes, 0, peer, static_cast<SphCtx *>(user)->nccl_comm, static_cast<cudaStream_t>(stream));
+}
+#endif
+
+// transport calls are host calls: under stream capture NCCL records its own kernels; the host-emulated build
+// records the call itself so that a graph replay repeats it
+#ifdef SPH_EMU
+#define TRANSPORT_OP(st, expr) emu::submit((st), [=]() { (void)(expr); })
+#else
+#define TRANSPORT_OP(st, expr)                                                                                  \
+    do {                                                                                                        \
+        int _rc = (expr);                                                                                       \
+        if (_rc) return fail(c, SPH_E_NCCL, std::string("halo exchange transport failed: ") + #expr + " -> " + std::to_string(_rc)); \
+    } while (0)
+#endif
+
+// One halo exchange: the packed staging of both sides goes out, the neighbours' records land behind the live
+// records of the CURRENT buffer set (left neighbour's at n - 2 * halo_cap, right neighbour's at n - halo_cap),
+// their headers in the device step state.  Fixed-size messages (the record count travels in the header), so the
+// whole group can be captured in a CUDA graph.
+int shard_exchange(SphCtx *c, cudaStream_t st) {
+    if (c->world <= 1) return SPH_OK;
+    if (!c->has_transport) return fail(c, SPH_E_ARG, "no transport: call sph_comm_init_nccl or sph_comm_set_transport first");
+    const SphTransport t = c->transport;
+    const DevArrays S = c->S;
+    const uint64_t bytes = (uint64_t)c->P.halo_cap * 16;
+    float4 *cur[4] = {S.posm, S.veld, S.x0id, S.misc};
+    TRANSPORT_OP(st, t.group_start(t.user));
+    for (int side = 0; side < 2; ++side) {
+        const int peer = side == 0 ? c->rank - 1 : c->rank + 1;
+        if (peer < 0 || peer >= c->world) continue;
+        const int64_t tail = (int64_t)c->P.n - (side == 0 ? 2 : 1) * (int64_t)c->P.halo_cap;
+        for (int k = 0; k < 4; ++k) {
+            const void *sp = S.stage[side][k];
+            void *rp = cur[k] + tail;
+            TRANSPORT_OP(st, t.send(t.user, sp, bytes, peer, st));
+            TRANSPORT_OP(st, t.recv(t.user, rp, bytes, peer, st));
+        }
+        const void *hs = S.stage_hdr[side];
+        void *hr = S.sd + (side == 0 ? SD_HDR_L : SD_HDR_R);
+        TRANSPORT_OP(st, t.send(t.user, hs, 64, peer, st));
+        TRANSPORT_OP(st, t.recv(t.user, hr, 64, peer, st));
+    }
+    TRANSPORT_OP(st, t.group_end(t.user, st));
+    return SPH_OK;
+}
+
+// plan -> classify + sort -> info -> [density -> boundary forces] -> pack -> { exchange || interior forces }
+// ev[5] (optional): CUDA events recorded at the stage boundaries (sph_shard_profile_step)
+int shard_sequence(SphCtx *c, cudaStream_t st, bool compute, int64_t *kernels, cudaEvent_t *ev = nullptr) {
+    if (ev) cudaEventRecord(ev[0], st);
+    k_shard_plan<<<1, 32, 0, st>>>(c->P, c->S);
+    *kernels += 1;
+    int rc = launch_neighbor_build(c, st, nullptr, kernels, /*move_acc=*/false);
     if (rc) return rc;
-    k_slab_info<<<1, 32, 0, st>>>(P, ctx->S, info_dev);
-    ctx->launches += 1;
-    CUDA_TRY(ctx, cudaGetLastError());
-    if (!sort_only) return sph_slab_compute(ctx, stream);
+    k_shard_info<<<1, 32, 0, st>>>(c->P, c->S);
+    *kernels += 1;
+    if (ev) cudaEventRecord(ev[1], st);
+    if (compute) {
+        launch_pair_density(c, st, kernels);
+        if (ev) cudaEventRecord(ev[2], st);
+        launch_pair_force_and_advect(c, st, nullptr, kernels, /*split_mode=*/1);  // the particles about to be sent
+    } else if (ev) {
+        cudaEventRecord(ev[2], st);
+    }
+    k_shard_pack<<<dim3(blocks_for(c->P.halo_cap, 256), 2), 256, 0, st>>>(c->P, c->S);
+    *kernels += 1;
+    CUDA_TRY(c, cudaGetLastError());
+    if (ev) cudaEventRecord(ev[3], st);
+    // the exchange for the NEXT step runs on the communication stream while the interior is still computed
+#ifdef SPH_EMU
+    cudaStream_t cs = st;  // the emulated runtime is synchronous
+#else
+    cudaStream_t cs = c->comm_stream;
+    CUDA_TRY(c, cudaEventRecord(c->ev_packed, st));
+    CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev_packed, 0));
+#endif
+    rc = shard_exchange(c, cs);
+    if (rc) return rc;
+    if (compute) launch_pair_force_and_advect(c, st, nullptr, kernels, /*split_mode=*/2);
+#ifndef SPH_EMU
+    CUDA_TRY(c, cudaEventRecord(c->ev_exchanged, cs));
+    CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_exchanged, 0));
+#endif
+    if (ev) cudaEventRecord(ev[4], st);
+    CUDA_TRY(c, cudaGetLastError());
+    c->built = false; c->list_valid = false;
     return SPH_OK;
 }
 
-// density / forces / integration of the owned particles after sph_slab_step(sort_only = 1)
-int sph_slab_compute(SphCtx *ctx, void *stream) {
+int capture_shard_step(SphCtx *ctx, cudaGraphExec_t *out, int64_t *kernels_out) {
+    const int par = ctx->parity;
+    cudaGraph_t g = nullptr;
+    int64_t kernels = 0;
+    if (!ctx->capture_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = ctx->capture_stream;
+    // relaxed: NCCL may issue CUDA calls of its own while its send / recv kernels are being captured
+    CUDA_TRY(ctx, cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+    int rc = shard_sequence(ctx, cs, /*compute=*/true, &kernels);
+    cudaError_t e = cudaStreamEndCapture(cs, &g);
+    ctx->parity = par;  // capture advanced the host-side parity exactly as a real step does; rewind
+    bind_arrays(ctx);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(ctx, SPH_E_CUDA, std::string("sharded graph capture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(ctx, SPH_E_CUDA, std::string("sharded graph instantiate: ") + cudaGetErrorString(e));
+    *kernels_out = kernels;
+    return SPH_OK;
+}
+
+}  // namespace
+extern "C" {
+
+int sph_comm_unique_id(char out128[128]) {
+#ifdef SPH_EMU
+    (void)out128;
+    return fail(nullptr, SPH_E_NCCL, "the host-emulated build has no NCCL: use sph_comm_set_transport");
+#else
+    if (!out128) return SPH_E_ARG;
+    if (!load_nccl()) return fail(nullptr, SPH_E_NCCL, g_nccl.err);
+    NcclId id;
+    int rc = g_nccl.GetUniqueId(&id);
+    if (rc) return fail(nullptr, SPH_E_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc));
+    std::memcpy(out128, id.internal, 128);
+    return SPH_OK;
+#endif
+}
+
+int sph_comm_init_nccl(SphCtx *ctx, const char id128[128], int32_t rank, int32_t world) {
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return SPH_E_ARG;
+#ifdef SPH_EMU
+    return fail(ctx, SPH_E_NCCL, "the host-emulated build has no NCCL: use sph_comm_set_transport");
+#else
+    if (!load_nccl()) return fail(ctx, SPH_E_NCCL, g_nccl.err);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    NcclId id;
+    std::memcpy(id.internal, id128, 128);
+    int rc = g_nccl.CommInitRank(&ctx->nccl_comm, world, id, rank);
+    if (rc) return fail(ctx, SPH_E_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc));
+    ctx->transport = SphTransport{ctx, nccl_group_start, nccl_group_end, nccl_send, nccl_recv};
+    ctx->has_transport = true;
+    ctx->rank = rank; ctx->world = world;
+    drop_graphs(ctx);
+    return SPH_OK;
+#endif
+}
+
+int sph_comm_set_transport(SphCtx *ctx, const SphTransport *t, int32_t rank, int32_t world) {
+    if (!ctx || world < 1 || rank < 0 || rank >= world) return SPH_E_ARG;
+    if (world > 1 && (!t || !t->group_start || !t->group_end || !t->send || !t->recv)) return fail(ctx, SPH_E_ARG, "incomplete transport");
+    if (t) ctx->transport = *t;
+    ctx->has_transport = t != nullptr;
+    ctx->rank = rank; ctx->world = world;
+    drop_graphs(ctx);
+    return SPH_OK;
+}
+
+int sph_shard_configure(SphCtx *ctx, int32_t x_lo, int32_t x_hi, int32_t ghost_layers, int64_t halo_capacity,
+                        int32_t rebalance_every) {
     if (!ctx) return SPH_E_ARG;
-    if (!ctx->P.slab_on) return fail(ctx, SPH_E_ARG, "sph_slab_configure was not called");
-    const DevParams &P = ctx->P;
-    if (P.n == 0) return SPH_OK;
-    if (!ctx->built) return fail(ctx, SPH_E_ARG, "sph_slab_compute needs a fresh sph_slab_step(sort_only = 1)");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (ctx->time_pair) {  // CUDA events around the two pair kernels (bench.py roofline at N > 1)
-        for (int k = 0; k < 3; ++k)
-            if (!ctx->pair_ev[k]) CUDA_TRY(ctx, cudaEventCreate(&ctx->pair_ev[k]));
-        cudaEventRecord(ctx->pair_ev[0], st);
-        launch_pair_density(ctx, st, &ctx->launches);
-        cudaEventRecord(ctx->pair_ev[1], st);
-        launch_pair_force_and_advect(ctx, st, nullptr, &ctx->launches);
-        cudaEventRecord(ctx->pair_ev[2], st);
-    } else {
-        launch_pair_density(ctx, st, &ctx->launches);
-        launch_pair_force_and_advect(ctx, st, nullptr, &ctx->launches);
+    if (x_lo < 0 || x_hi > ctx->P.gx || ghost_layers < 1 || x_hi - x_lo < ghost_layers + 2)
+        return fail(ctx, SPH_E_ARG, "slab must lie inside the grid and be at least ghost_layers + 2 cell layers wide");
+    if (!ctx->bodies.empty() || ctx->P.n_solid > 0)
+        return fail(ctx, SPH_E_ARG, "x-slab sharding supports fluid-only scenes (rigid bodies are single-GPU, SURVEY 8e)");
+    if (!ctx->P.uniform_fluid || ctx->P.dfsph)
+        return fail(ctx, SPH_E_ARG, "x-slab sharding needs the uniform-fluid WCSPH step (one fluid density)");
+    if (halo_capacity < 1 || 2 * halo_capacity + ctx->P.n > ctx->n_max)
+        return fail(ctx, SPH_E_CAPACITY, "capacity: packed particles + 2 * halo_capacity receive slots exceed n_max");
+    if (rebalance_every < 0) return SPH_E_ARG;
+    const int32_t n_mine = ctx->P.n;
+    drop_graphs(ctx);
+    if (ctx->shard_buf) { cudaFree(ctx->shard_buf); ctx->shard_buf = nullptr; }
+    const uint64_t bytes = 256 + 2 * 256 + 8 * align_up((uint64_t)halo_capacity * 16, 256);
+    CUDA_TRY(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->shard_buf), bytes));
+    CUDA_TRY(ctx, cudaMemset(ctx->shard_buf, 0, bytes));
+    int32_t sd[SD_INTS] = {0};
+    sd[SD_N_LIVE] = n_mine; sd[SD_OWNED] = n_mine; sd[SD_SX0] = x_lo; sd[SD_SX1] = x_hi;
+    CUDA_TRY(ctx, cudaMemcpy(ctx->shard_buf, sd, sizeof(sd), cudaMemcpyHostToDevice));
+    ctx->P.slab_on = 1; ctx->P.sgw = ghost_layers; ctx->P.halo_cap = (int32_t)halo_capacity;
+    ctx->P.has_left = ctx->rank > 0; ctx->P.has_right = ctx->rank + 1 < ctx->world;
+    ctx->P.rebalance_every = rebalance_every;
+    ctx->P.n = (int32_t)ctx->n_max;  // from here on n is the CAPACITY; the live count is device state
+    ctx->shard_begun = false;
+    bind_arrays(ctx);
+#ifndef SPH_EMU
+    if (!ctx->comm_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // the exchange must get SMs while the interior pass runs
+        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_packed, cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_exchanged, cudaEventDisableTiming));
     }
-    ctx->built = false; ctx->list_valid = false;
-    CUDA_TRY(ctx, cudaGetLastError());
+#endif
     return SPH_OK;
 }
 
-// sph_slab_compute in two phases so that the caller can start the next halo exchange in between:
-// phase 0 = density pass + forces/integration of the particles inside this rank's (wide) send ranges,
-// phase 1 = forces/integration of all other owned particles.  info_dev is the array sph_slab_step wrote.
-int sph_slab_compute_split(SphCtx *ctx, const int32_t *info_dev, int32_t phase, void *stream) {
-    if (!ctx || !info_dev || (phase != 0 && phase != 1)) return SPH_E_ARG;
-    if (!ctx->P.slab_on) return fail(ctx, SPH_E_ARG, "sph_slab_configure was not called");
-    const DevParams &P = ctx->P;
-    if (P.n == 0) return SPH_OK;
-    if (!(P.uniform_fluid && ctx->var_force != 0))
-        return fail(ctx, SPH_E_ARG, "split compute needs the uniform-fluid force kernel; use sph_slab_compute");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (phase == 0) {
-        if (!ctx->built) return fail(ctx, SPH_E_ARG, "sph_slab_compute_split needs a fresh sph_slab_step(sort_only = 1)");
-        launch_pair_density(ctx, st, &ctx->launches);
-        launch_pair_force_and_advect(ctx, st, nullptr, &ctx->launches, info_dev, 0);
-    } else {
-        launch_pair_force_and_advect(ctx, st, nullptr, &ctx->launches, info_dev, 1);
-        ctx->built = false; ctx->list_valid = false;
-    }
-    CUDA_TRY(ctx, cudaGetLastError());
+#define REQUIRE_SHARD(ctx)                                                                              \
+    if (!(ctx)) return SPH_E_ARG;                                                                       \
+    if (!(ctx)->P.slab_on || !(ctx)->shard_buf) return fail((ctx), SPH_E_ARG, "sph_shard_configure was not called");
+
+int sph_shard_begin(SphCtx *ctx, void *stream) {
+    REQUIRE_SHARD(ctx);
+    int rc = shard_sequence(ctx, static_cast<cudaStream_t>(stream), /*compute=*/false, &ctx->launches);
+    if (rc) return rc;
+    ctx->shard_begun = true;
     return SPH_OK;
 }
 
-// Enable / read the CUDA-event timing of the last sph_slab_compute: ms_out = {density, force}.
-// Reading synchronises on the recorded events.
-int sph_slab_pair_times(SphCtx *ctx, int32_t enable, float *ms_out) {
-    if (!ctx) return SPH_E_ARG;
-    if (ms_out && ctx->time_pair && ctx->pair_ev[2]) {
-        CUDA_TRY(ctx, cudaEventSynchronize(ctx->pair_ev[2]));
-        CUDA_TRY(ctx, cudaEventElapsedTime(&ms_out[0], ctx->pair_ev[0], ctx->pair_ev[1]));
-        CUDA_TRY(ctx, cudaEventElapsedTime(&ms_out[1], ctx->pair_ev[1], ctx->pair_ev[2]));
+int sph_halo_exchange(SphCtx *ctx, void *stream) {
+    REQUIRE_SHARD(ctx);
+    return shard_exchange(ctx, static_cast<cudaStream_t>(stream));
+}
+
+int sph_shard_step(SphCtx *ctx, int32_t nsteps, void *stream) {
+    REQUIRE_SHARD(ctx);
+    if (nsteps < 0) return SPH_E_ARG;
+    if (!ctx->shard_begun) return fail(ctx, SPH_E_ARG, "sph_shard_begin was not called");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int s = 0; s < nsteps; ++s) {
+        const int par = ctx->parity;
+        if (!ctx->graph_shard[par]) {
+            int rc = capture_shard_step(ctx, &ctx->graph_shard[par], &ctx->graph_shard_kernels[par]);
+            if (rc) return rc;
+        }
+        CUDA_TRY(ctx, cudaGraphLaunch(ctx->graph_shard[par], st));
+        ctx->launches += ctx->graph_shard_kernels[par];
+        ctx->parity = par ^ 1;
+        bind_arrays(ctx);
     }
-    ctx->time_pair = enable != 0;
+    return SPH_OK;
+}
+
+int sph_shard_info(SphCtx *ctx, int32_t *out16, uint64_t *out_sent, void *stream) {
+    REQUIRE_SHARD(ctx);
+    if (!out16) return SPH_E_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t sd[SD_INTS];
+    uint32_t status = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(sd, ctx->S.sd, sizeof(sd), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(&status, ctx->S.status, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    for (int k = 0; k < 14; ++k) out16[k] = sd[k];
+    out16[14] = (int32_t)status; out16[15] = 0;
+    if (out_sent) *out_sent = ((uint64_t)(uint32_t)sd[SD_SENT_HI] << 32) | (uint32_t)sd[SD_SENT_LO];
+    return SPH_OK;
+}
+
+int sph_shard_profile_step(SphCtx *ctx, float *ms_out4, void *stream) {
+    REQUIRE_SHARD(ctx);
+    if (!ms_out4) return SPH_E_ARG;
+    if (!ctx->shard_begun) return fail(ctx, SPH_E_ARG, "sph_shard_begin was not called");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaEvent_t ev[5];
+    for (int k = 0; k < 5; ++k) CUDA_TRY(ctx, cudaEventCreate(&ev[k]));
+    int rc = shard_sequence(ctx, st, /*compute=*/true, &ctx->launches, ev);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms_out4[k], ev[k], ev[k + 1]);
+    for (int k = 0; k < 5; ++k) cudaEventDestroy(ev[k]);
     return SPH_OK;
 }
 

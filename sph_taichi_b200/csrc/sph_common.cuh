@@ -47,16 +47,22 @@ struct DevParams {
     float k_w, k2_w, k_dw, w0, w_diam;
     float k1_grad, wd_norm;  // 6k / h and W(diameter) / 2k: normalisations of spline_pair()
     float pad, hi_x, hi_y, hi_z;
-    // x-slab sharding (multi-GPU): this rank owns cell layers [sx0, sx1) and keeps sgw ghost
-    // layers per side.  Records [n_local, n) were just received from the neighbour ranks.
-    int32_t slab_on, sx0, sx1, sgw, n_local;
+    // x-slab sharding (multi-GPU, sph_shard_*): this rank keeps sgw ghost layers per side; the slab [sx0, sx1)
+    // itself, the live count and the send / receive ranges live in DEVICE memory (DevArrays::sd) so that a whole
+    // sharded step -- sort, pair passes and halo exchange -- replays from one CUDA graph without the host.
+    // In this mode n is the CAPACITY of the arrays; the last 2 * halo_cap records are the receive regions
+    // (left neighbour, then right neighbour).
+    int32_t slab_on, sgw, halo_cap, has_left, has_right, rebalance_every;
     // all fluid particles share one mass and one volume (true for every scene the reference can
     // express with a single fluid density): the force pass then needs only 2 x 16 B per neighbour
     int32_t uniform_fluid;
     float fluid_m, fluid_mV;
     int32_t dfsph;  // simulationMethod 4: the density pass neither clamps nor evaluates the EOS
     int32_t opaque_zero;  // always 0; lets a kernel state a scheduling dependency ptxas cannot fold away
-    unsigned long long col_order;  // density v10: nibble p = the (dx, dy) column visited p-th
+    // nibble p = the (dx, dy) column c = (dx + 1) * 3 + (dy + 1) the density pass visits p-th.  The list order is
+    // free (only the summation order of the pair passes depends on it); centre column first makes the lanes of
+    // a warp gather the SAME records at the same time in the force pass (profiles/r02_column_order.txt)
+    unsigned long long col_order;
 };
 
 struct DevArrays {
@@ -84,11 +90,34 @@ struct DevArrays {
     int32_t *nbr_list;
     int32_t *nbr_cnt;
     int32_t npad;
-    // SoA copy of posm = {x, y, z, m_V} (written by k_rank_move, m_V patched by k_boundary_volume; valid while
-    // `built`): the density scan reads FOUR consecutive candidates per 128-bit load from each row (rows are
-    // padded by 32 floats)
-    float *sx, *sy, *sz, *sw;  // x, y, z, m_V
+    // x-slab sharding: device-resident step state (SD_* below) and the send staging of the two sides
+    // (0 = to the left neighbour, 1 = to the right): 4 record arrays of halo_cap entries + a 16-int header
+    int32_t *sd;
+    float4 *stage[2][4];
+    int32_t *stage_hdr[2];
 };
+
+// DevArrays::sd (ints).  Header layout (sent with every exchange): {records, owned, sx0, sx1, step}.
+enum {
+    SD_N_LIVE = 0,   // sorted records [0, n_live) are owned or ghost; [n_live, n_sorted) is the trash bucket
+    SD_OWNED, SD_SX0, SD_SX1, SD_STEP,
+    SD_OWN0, SD_OWN1,                            // index range of the owned cell layers
+    SD_SEND_L0, SD_SEND_L1, SD_SEND_R0, SD_SEND_R1,  // index ranges packed for the left / right neighbour
+    SD_RECV_L, SD_RECV_R,                        // records received for THIS step's classification
+    SD_N_SORTED, SD_FLAGS, SD_SPARE,
+    SD_HDR_L = 16, SD_HDR_R = 32,                // headers received from the left / right neighbour
+    SD_SENT_LO = 48, SD_SENT_HI,                 // records sent so far (64-bit, for the halo statistics)
+    SD_INTS = 64
+};
+constexpr int SHARD_MIN_WIDTH = 5;  // a slab gives a layer away only while it is wider than this (ghost band 2 + send range 4 must fit)
+
+// Is record i an input of this step's classification?  (live records of the last sort + what the halo
+// exchange delivered behind them)
+__device__ __forceinline__ bool shard_input_valid(const DevParams &P, const int32_t *__restrict__ sd, int i) {
+    if (i < sd[SD_N_LIVE]) return true;
+    const int rl = P.n - 2 * P.halo_cap, rr = P.n - P.halo_cap;
+    return (i >= rl && i < rl + sd[SD_RECV_L]) || (i >= rr && i < rr + sd[SD_RECV_R]);
+}
 
 constexpr int NBR_CAP = 96;  // soak runs of the shipped scenes peak at 54 neighbours (tools/soak.py)
 constexpr int NBR_OVERFLOW = 0x7fffffff;
@@ -256,6 +285,6 @@ inline void derive_dev_params(DevParams &P, const SphParams &h) {
     }
     P.k1_grad = P.k_dw * P.inv_h; P.wd_norm = P.w_diam / P.k2_w;
     P.opaque_zero = 0;
-    if (P.col_order == 0ull) P.col_order = 0x876543210ull;  // raster order (the reference's) unless set before
+    if (P.col_order == 0ull) P.col_order = 0x862075314ull;  // centre, edges, corners (4 1 3 5 7 0 2 6 8)
     P.pad = h.h; P.hi_x = h.clamp_hi[0]; P.hi_y = h.clamp_hi[1]; P.hi_z = h.clamp_hi[2];
 }

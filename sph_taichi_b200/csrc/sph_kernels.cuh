@@ -65,7 +65,8 @@ __global__ void k_upload_xv(DevParams P, DevArrays S, const float *x, const floa
 // =====================================================================================
 __global__ void k_hash_count(DevParams P, DevArrays S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < P.n;
+    // sharded: the inputs are the live records of the last sort and what the halo exchange delivered
+    const bool active = i < P.n && (!P.slab_on || shard_input_valid(P, S.sd, i));
     int c = -1;
     if (active) {
         float4 p = S.posm[i];
@@ -83,13 +84,14 @@ __global__ void k_hash_count(DevParams P, DevArrays S) {
             // Ownership is a pure function of the (bitwise identical) position on both ranks, so a
             // particle is owned by exactly one rank.  Everything that is neither owned nor inside
             // the ghost band goes to the trash bucket C, which sorts to the end.
+            const int sx0 = S.sd[SD_SX0], sx1 = S.sd[SD_SX1];
             float4 m = S.misc[i];
             uint32_t fl = __float_as_uint(m.z);
-            bool in_slab = ci >= P.sx0 && ci < P.sx1;
-            bool in_band = ci >= P.sx0 - P.sgw && ci < P.sx1 + P.sgw;
+            bool in_slab = ci >= sx0 && ci < sx1;
+            bool in_band = ci >= sx0 - P.sgw && ci < sx1 + P.sgw;
             bool was_ghost = (fl & FLAG_GHOST) != 0;
             if (was_ghost) {
-                c = P.C;  // last step's ghosts (local) or a neighbour's ghost (received): drop
+                c = P.C;  // last step's ghosts: dropped (the neighbour sends fresh copies every step)
             } else if (in_slab) {
                 // stays / becomes owned
             } else if (in_band) {
@@ -116,29 +118,88 @@ __global__ void k_hash_count(DevParams P, DevArrays S) {
     }
 }
 
-// After the sort: live count and the index ranges of the boundary layers this rank must send
-// next step (layers [sx0, sx0+sgw+1) to the left neighbour, [sx1-sgw-1, sx1) to the right one).
-__global__ void k_slab_info(DevParams P, DevArrays S, int32_t *info) {
+// ---- x-slab sharding: the per-step bookkeeping that used to live on the host (round 1: an all-gather of the
+// info rows, a D2H copy and a host wait every step) -- three one-warp kernels inside the step graph ----
+
+// Before the classification: take the record counts out of the headers the halo exchange delivered and, every
+// `rebalance_every` steps, move the slab cuts by one layer toward the heavier side.  Both ranks of a cut hold
+// the same four integers (their own and the neighbour's owned count and width, exchanged in the headers) and
+// evaluate the same integer expression, so they always agree -- no extra message.
+__device__ __forceinline__ int shard_cut_move(long long owned_l, int width_l, long long owned_r, int width_r) {
+    // the cut moves one layer toward the heavier side when the difference exceeds ~1.2 layers' worth
+    if ((owned_l - owned_r) * 5 * width_l > 6 * owned_l && width_l > SHARD_MIN_WIDTH) return -1;
+    if ((owned_r - owned_l) * 5 * width_r > 6 * owned_r && width_r > SHARD_MIN_WIDTH) return +1;
+    return 0;
+}
+__global__ void k_shard_plan(DevParams P, DevArrays S) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int32_t *sd = S.sd;
+    const int32_t *hl = sd + SD_HDR_L, *hr = sd + SD_HDR_R;
+    const int step = sd[SD_STEP];
+    sd[SD_RECV_L] = P.has_left ? min(hl[0], P.halo_cap) : 0;
+    sd[SD_RECV_R] = P.has_right ? min(hr[0], P.halo_cap) : 0;
+    if (P.rebalance_every > 0 && step > 0 && step % P.rebalance_every == 0) {
+        const int sx0 = sd[SD_SX0], sx1 = sd[SD_SX1], owned = sd[SD_OWNED];
+        int n0 = sx0, n1 = sx1;
+        if (P.has_left) n0 += shard_cut_move(hl[1], hl[3] - hl[2], owned, sx1 - sx0);
+        if (P.has_right) n1 += shard_cut_move(owned, sx1 - sx0, hr[1], hr[3] - hr[2]);
+        sd[SD_SX0] = n0; sd[SD_SX1] = n1;
+    }
+    sd[SD_STEP] = step + 1;
+}
+
+// After the sort: live count, owned range and the index ranges of the boundary layers to send (sgw + 2 layers
+// per side: one more than the ghost band needs, so that a cut may move by a layer in any step), and the headers.
+__global__ void k_shard_info(DevParams P, DevArrays S) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int32_t *sd = S.sd;
     const int layer = P.gy * P.gz;
+    const int sx0 = sd[SD_SX0], sx1 = sd[SD_SX1];
     auto start_of_layer = [&](int L) {
         L = min(max(L, 0), P.gx);
         int c = L * layer;
         return c > 0 ? S.cell_end[c - 1] : 0;
     };
-    info[0] = S.cell_end[P.C - 1];                      // live particles (owned + ghosts)
-    info[1] = start_of_layer(P.sx0);                    // left send range
-    info[2] = start_of_layer(min(P.sx0 + P.sgw + 1, P.sx1));
-    info[3] = start_of_layer(max(P.sx1 - P.sgw - 1, P.sx0));  // right send range
-    info[4] = start_of_layer(P.sx1);
-    info[5] = P.n;                                      // records processed (live + trash)
-    info[6] = info[4] - info[1];                        // owned particles
-    info[7] = (int32_t)(*S.status);
-    // one layer wider, used on the steps where the slab cut between two ranks moves by a layer
-    info[8] = start_of_layer(min(P.sx0 + P.sgw + 2, P.sx1));
-    info[9] = start_of_layer(max(P.sx1 - P.sgw - 2, P.sx0));
-    info[10] = P.sx0;
-    info[11] = P.sx1;
+    const int n_live = S.cell_end[P.C - 1], n_sorted = S.cell_end[P.C];
+    const int o0 = start_of_layer(sx0), o1 = start_of_layer(sx1);
+    int l0 = o0, l1 = start_of_layer(min(sx0 + P.sgw + 2, sx1));
+    int r0 = start_of_layer(max(sx1 - P.sgw - 2, sx0)), r1 = o1;
+    if (!P.has_left) l1 = l0;
+    if (!P.has_right) r0 = r1;
+    uint32_t flags = 0u;
+    if (l1 - l0 > P.halo_cap) { l1 = l0 + P.halo_cap; flags |= SPH_STATUS_HALO_CAPACITY; }
+    if (r1 - r0 > P.halo_cap) { r0 = r1 - P.halo_cap; flags |= SPH_STATUS_HALO_CAPACITY; }
+    if (n_sorted > P.n - 2 * P.halo_cap) flags |= SPH_STATUS_SHARD_CAPACITY;  // the sort ran into the receive regions
+    if (flags) atomicOr(S.status, flags);
+    sd[SD_N_LIVE] = n_live; sd[SD_N_SORTED] = n_sorted;
+    sd[SD_OWNED] = o1 - o0; sd[SD_OWN0] = o0; sd[SD_OWN1] = o1;
+    sd[SD_SEND_L0] = l0; sd[SD_SEND_L1] = l1; sd[SD_SEND_R0] = r0; sd[SD_SEND_R1] = r1;
+    sd[SD_FLAGS] = (int32_t)(*S.status);
+    unsigned long long sent = ((unsigned long long)(uint32_t)sd[SD_SENT_HI] << 32) | (uint32_t)sd[SD_SENT_LO];
+    sent += (unsigned long long)(l1 - l0) + (unsigned long long)(r1 - r0);
+    sd[SD_SENT_LO] = (int32_t)(uint32_t)sent; sd[SD_SENT_HI] = (int32_t)(uint32_t)(sent >> 32);
+    for (int side = 0; side < 2; ++side) {
+        int32_t *h = S.stage_hdr[side];
+        h[0] = side == 0 ? l1 - l0 : r1 - r0;
+        h[1] = o1 - o0; h[2] = sx0; h[3] = sx1; h[4] = sd[SD_STEP];
+    }
+}
+
+// Pack the (already advanced) boundary particles into the send staging: slot s of side 0 is record l0 + s, of
+// side 1 record r0 + s.  acc is not exchanged (recomputed every step).
+__global__ void k_shard_pack(DevParams P, DevArrays S) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int side = blockIdx.y;
+    const int32_t *sd = S.sd;
+    const int b = side == 0 ? sd[SD_SEND_L0] : sd[SD_SEND_R0];
+    const int e = side == 0 ? sd[SD_SEND_L1] : sd[SD_SEND_R1];
+    if (s >= e - b) return;
+    const int i = b + s;
+    SPH_EMU_CHECK(s < P.halo_cap && i >= 0 && i < P.n);
+    S.stage[side][0][s] = S.posm[i];
+    S.stage[side][1][s] = S.veld[i];
+    S.stage[side][2][s] = S.x0id[i];
+    S.stage[side][3][s] = S.misc[i];
 }
 
 // In-place inclusive prefix sum over the per-cell counts (the reference's
@@ -238,6 +299,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int32_t *__restrict__ dat
 __global__ void k_bucket(DevParams P, DevArrays S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
+    if (P.slab_on && !shard_input_valid(P, S.sd, i)) return;
     int c = S.cid[i];
     int start = c > 0 ? S.cell_end[c - 1] : 0;
     S.perm[start + S.ticket[i]] = i;
@@ -251,6 +313,7 @@ template <bool MOVE_ACC>
 __global__ void k_rank_move(DevParams P, DevArrays S) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.n) return;
+    if (P.slab_on && t >= S.cell_end[P.C]) return;  // sharded: P.n is the capacity, cell_end[C] the record count
     int src = S.perm[t];
     int c = S.cid[src];
     int a = c > 0 ? S.cell_end[c - 1] : 0;
@@ -262,9 +325,7 @@ __global__ void k_rank_move(DevParams P, DevArrays S) {
         dst = a + rank;
     }
     float4 misc = S.misc[src];
-    const float4 pm = S.posm[src];
-    S.posm_n[dst] = pm;
-    S.sx[dst] = pm.x; S.sy[dst] = pm.y; S.sz[dst] = pm.z; S.sw[dst] = pm.w;
+    S.posm_n[dst] = S.posm[src];
     S.veld_n[dst] = S.veld[src];
     S.x0id_n[dst] = S.x0id[src];
     S.misc_n[dst] = misc;
@@ -319,11 +380,7 @@ __global__ void __launch_bounds__(128) k_boundary_volume(DevParams P, DevArrays 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     // only .w changes; concurrent readers use .xyz only
-    if (lane == 0) {
-        const float mv = 1.0f / (P.w0 + part) * 3.0f;
-        reinterpret_cast<float *>(S.posm + i)[3] = mv;
-        S.sw[i] = mv;  // the SoA copy the density scan reads
-    }
+    if (lane == 0) reinterpret_cast<float *>(S.posm + i)[3] = 1.0f / (P.w0 + part) * 3.0f;
 }
 
 // Densities (WCSPH.py:33-43).  FUSE_EOS additionally applies the clamp + Tait EOS of
@@ -468,7 +525,7 @@ __global__ void k_advect(DevParams P, DevArrays S) {
     if (i >= P.n) return;
     uint32_t fl = __float_as_uint(S.misc[i].z);
     if (!(fl & FLAG_DYNAMIC) || (fl & FLAG_GHOST)) return;
-    if (P.slab_on && S.grid_ids[i] >= P.C) return;
+    if (P.slab_on && i >= S.sd[SD_N_LIVE]) return;
     float4 p = S.posm[i], v = S.veld[i], a = S.acc[i];
     v.x += P.dt * a.x; v.y += P.dt * a.y; v.z += P.dt * a.z;
     p.x += P.dt * v.x; p.y += P.dt * v.y; p.z += P.dt * v.z;
@@ -740,7 +797,7 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
     mbar_fence_init();
     __syncwarp();
 
-    bool live = i < P.n && !(P.slab_on && S.grid_ids[min(i, P.n - 1)] >= P.C);
+    bool live = i < (P.slab_on ? S.sd[SD_N_LIVE] : P.n);  // sharded: the trash bucket behind n_live is not touched
     float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), mi = pi;
     uint32_t fl = 0;
     if (live) { pi = S.posm[i]; mi = S.misc[i]; fl = __float_as_uint(mi.z); }
@@ -762,8 +819,9 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
     cell_of(P, pi.x, pi.y, pi.z, ci, cj, ck);
     ci = min(max(ci, 0), P.gx - 1); cj = min(max(cj, 0), P.gy - 1); ck = min(max(ck, 0), P.gz - 1);
     const int k_lo = max(ck - 1, 0), k_hi = min(ck + 1, P.gz - 1);
-    // per-lane candidate range of column c = (dx + 1) * 3 + (dy + 1), reference visiting order
-    auto col_range = [&](int c, int &j0, int &j1) {
+    // per-lane candidate range of the p-th visited column c = (dx + 1) * 3 + (dy + 1) (DevParams::col_order)
+    auto col_range = [&](int p, int &j0, int &j1) {
+        const int c = (int)((P.col_order >> (4 * p)) & 15ull);
         int ni = ci + c / 3 - 1, nj = cj + c % 3 - 1;
         j0 = 0; j1 = 0;
         if (fluid && ni >= 0 && ni < P.gx && nj >= 0 && nj < P.gy) {
@@ -904,284 +962,12 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Density pass v10: SoA candidate quads, one coalesced cell_end load per column.
-//
-// What the v8 profile showed (profiles/r02_density_v8_source_breakdown.txt): per warp 5266 instructions =
-// 670 per-column set-up (18 dependent cell_end loads, 2 CREDUX, spilled window state) + 1937 scan + 2065 hit
-// loop; and the L1/shared pipe at 80 %: an AoS LDS.128 per candidate costs 5.8 wavefronts because the lanes
-// of a warp sit in 4-5 cells whose windows start ~128 bytes apart (same banks).  Here:
-//  * positions are read from the per-step SoA rows sx / sy / sz (k_rank_move writes them): one 128-bit load
-//    per row delivers FOUR consecutive candidates, the lanes' addresses are ~32 bytes apart (different banks /
-//    one or two L1 lines), 0.75 loads per candidate instead of 1;
-//  * a warp's 32 consecutive particles sit in ONE (x, y) column of cells (fast path, checked): the cell_end
-//    entries all lanes need for a neighbour column are `span + 3` consecutive words -- one coalesced load by
-//    the first lanes, each lane picks its two range ends with shuffles; the next column's load is issued
-//    before the current column is processed;
-//  * no staging: the windows of a warp are ~6 KB and stay in L1; TMA copies of ~200 bytes each cost more
-//    issue slots than they hide latency (profiles/r02_parked_variants_sweep.txt).
-// Output (lists, densities, EOS, fpv) is identical to k_density_tma: same candidates, same visiting order.
-#ifndef DENS10_THREADS
-#define DENS10_THREADS 128
-#endif
-#ifndef DENS10_MIN_BLOCKS
-#define DENS10_MIN_BLOCKS 8
-#endif
-#ifndef DENS10_SLOTS
-#define DENS10_SLOTS 12  // nine columns + the occasional second chunk of a long column
-#endif
-#ifndef DENS10_PACKED
-#define DENS10_PACKED 0  // 1: FADD2 / FFMA2 on the (x, y) (z, w) halves of a quad
-#endif
-// Column visiting order (DevParams::col_order, one nibble per position): the list order is free -- only the
-// summation order of the two pair passes depends on it -- and the force pass gathers measurably faster when the
-// nine (dx, dy) columns are not walked in raster order (profiles/r02_column_order.txt).
-__device__ __forceinline__ int dens10_column(const DevParams &P, int p) { return (int)((P.col_order >> (4 * p)) & 15ull); }
-__device__ __forceinline__ float4 ldg_quad(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-
-// distance pre-filter of up to 32 candidates jb .. jb + len - 1 (jb a multiple of 4), eight per step:
-// candidate u ends up in bit len - 1 - u (the sign of |r|^2 - h2_scan is funnel-shifted in)
-__device__ __forceinline__ uint32_t scan_soa(const DevParams &P, const float *__restrict__ sx,
-                                             const float *__restrict__ sy, const float *__restrict__ sz, int jb, int len,
-                                             float xi, float yi, float zi) {
-    uint32_t m = 0u;
-    int done = 0;
-#if DENS10_PACKED
-    const f32x2 nx = pack2(-xi, -xi), ny = pack2(-yi, -yi), nz = pack2(-zi, -zi), nh = pack2(-P.h2_scan, -P.h2_scan);
-#endif
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        if (g * 8 < len) {
-            const float4 X0 = ldg_quad(sx + jb + g * 8), X1 = ldg_quad(sx + jb + g * 8 + 4);
-            const float4 Y0 = ldg_quad(sy + jb + g * 8), Y1 = ldg_quad(sy + jb + g * 8 + 4);
-            const float4 Z0 = ldg_quad(sz + jb + g * 8), Z1 = ldg_quad(sz + jb + g * 8 + 4);
-#if DENS10_PACKED
-            auto two = [&](float xa, float xb, float ya, float yb, float za, float zb) {
-                f32x2 rx = add2(pack2(xa, xb), nx), ry = add2(pack2(ya, yb), ny), rz = add2(pack2(za, zb), nz);
-                f32x2 d = fma2(rz, rz, fma2(ry, ry, fma2(rx, rx, nh)));
-                m = __funnelshift_l((uint32_t)d, m, 1);
-                m = __funnelshift_l((uint32_t)(d >> 32), m, 1);
-            };
-            two(X0.x, X0.y, Y0.x, Y0.y, Z0.x, Z0.y); two(X0.z, X0.w, Y0.z, Y0.w, Z0.z, Z0.w);
-            two(X1.x, X1.y, Y1.x, Y1.y, Z1.x, Z1.y); two(X1.z, X1.w, Y1.z, Y1.w, Z1.z, Z1.w);
-#else
-            auto one = [&](float x, float y, float z) {
-                float rx = xi - x, ry = yi - y, rz = zi - z;
-                float d = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, -P.h2_scan)));
-                m = __funnelshift_l(__float_as_uint(d), m, 1);
-            };
-            one(X0.x, Y0.x, Z0.x); one(X0.y, Y0.y, Z0.y); one(X0.z, Y0.z, Z0.z); one(X0.w, Y0.w, Z0.w);
-            one(X1.x, Y1.x, Z1.x); one(X1.y, Y1.y, Z1.y); one(X1.z, Y1.z, Z1.z); one(X1.w, Y1.w, Z1.w);
-#endif
-            done = g * 8 + 8;
-        }
-    }
-    return m >> (done - len);
-}
-
-template <bool FASTW>
-__global__ void __launch_bounds__(DENS10_THREADS, DENS10_MIN_BLOCKS) k_density_soa(DevParams P, DevArrays S) {
-    __shared__ uint32_t s_m[DENS10_SLOTS][DENS10_THREADS];   // per-thread slots: hit masks of the scanned chunks
-    __shared__ int32_t s_top[DENS10_SLOTS][DENS10_THREADS];  // and the candidate index of bit 0
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = i < P.n && !(P.slab_on && S.grid_ids[min(i, P.n - 1)] >= P.C);
-    float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), mi = pi;
-    uint32_t fl = 0;
-    if (live) { pi = S.posm[i]; mi = S.misc[i]; fl = __float_as_uint(mi.z); }
-    const bool fluid = live && (fl & FLAG_FLUID);
-    if (live && !fluid) {
-        bool dyn = (fl & FLAG_DYNAMIC) != 0;
-        float4 vb = S.veld[i];
-        S.aux[i] = make_float4(vb.w, 0.0f, dyn ? -2.0f : -1.0f, 0.0f);
-        if (!P.dfsph) S.acc[i] = dyn ? make_float4(P.gx_, P.gy_, P.gz_, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
-        S.nbr_cnt[i] = 0;
-        if (P.uniform_fluid) {
-            S.fpv[2 * (size_t)i] = pi;  // w = m_V of the boundary particle
-            S.fpv[2 * (size_t)i + 1] = make_float4(vb.x, vb.y, vb.z, dyn ? -vb.w : -__int_as_float(0x7f800000));
-        }
-    }
-    if (__ballot_sync(0xffffffffu, fluid) == 0u) return;  // warp-uniform
-
-    int ci = 0, cj = 0, ck = 0;
-    cell_of(P, pi.x, pi.y, pi.z, ci, cj, ck);
-    ci = min(max(ci, 0), P.gx - 1); cj = min(max(cj, 0), P.gy - 1); ck = min(max(ck, 0), P.gz - 1);
-    const int k_lo = max(ck - 1, 0), k_hi = min(ck + 1, P.gz - 1);
-    // fast path: all fluid lanes in one (x, y) column of cells and few enough z-cells for one load per column
-    const int colkey = ci * P.gy + cj;
-    const int key_lo = __reduce_min_sync(0xffffffffu, fluid ? colkey : 0x7fffffff);
-    const int key_hi = __reduce_max_sync(0xffffffffu, fluid ? colkey : -1);
-    const int kmin = __reduce_min_sync(0xffffffffu, fluid ? ck : 0x7fffffff);
-    const int kmax = __reduce_max_sync(0xffffffffu, fluid ? ck : -1);
-    const bool fast = key_lo == key_hi && kmax - kmin + 4 <= 32;
-    const int ci_u = key_lo / P.gy, cj_u = key_lo - ci_u * P.gy;
-    // fast path: lane L holds cell_end[row_c + kmin - 2 + L] of the column being prepared; a lane's range ends are
-    // entries k_lo - kmin + 1 and k_hi - kmin + 2 (particle_system.py:383: [prefix[max(c_lo - 1, 0)], prefix[c_hi]))
-    auto col_entry = [&](int c) -> int {
-        const int ni = ci_u + c / 3 - 1, nj = cj_u + c % 3 - 1;
-        if (ni < 0 || ni >= P.gx || nj < 0 || nj >= P.gy) return -1;  // column outside the grid: empty range
-        const int row = (ni * P.gy + nj) * P.gz;
-        const int idx = min(max(row + kmin - 2 + lane, 0), row + P.gz - 1);
-        return __ldg(S.cell_end + idx);
-    };
-    auto col_range_slow = [&](int c, int &j0, int &j1) {
-        int ni = ci + c / 3 - 1, nj = cj + c % 3 - 1;
-        j0 = 0; j1 = 0;
-        if (fluid && ni >= 0 && ni < P.gx && nj >= 0 && nj < P.gy) {
-            int row = (ni * P.gy + nj) * P.gz;
-            j0 = __ldg(S.cell_end + max(row + k_lo - 1, 0));
-            j1 = __ldg(S.cell_end + row + k_hi);
-        }
-    };
-
-    int cnt = 0;
-    float den = 0.0f;
-    uint32_t widx = (uint32_t)(fluid ? i : 0);  // index of the next list slot
-    const uint32_t widx_cap = widx + (uint32_t)(NBR_CAP - 1) * (uint32_t)S.npad;  // last row
-    // one pre-filtered candidate: the exact `norm() < h` of the reference, list append, density contribution
-    auto visit = [&](int j, const float4 &pj) {
-        SPH_EMU_CHECK(j >= 0 && j < P.n);
-        float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-        float r2 = exact_r2(rx, ry, rz);
-        if (r2 < P.h2) {
-            SPH_EMU_CHECK((uint64_t)widx < (uint64_t)NBR_CAP * (uint64_t)S.npad);
-            S.nbr_list[widx] = j;  // beyond NBR_CAP the last row is overwritten (flagged below)
-            widx = min(widx + (uint32_t)S.npad, widx_cap);
-            ++cnt;
-            if (FASTW) {
-                den = fmaf(pj.w, spline_w_norm(P, r2), den);
-            } else {
-                float r, inv_r;
-                fast_norm(r2, r, inv_r);
-                den += pj.w * w_cubic(P, r);
-            }
-        }
-    };
-
-    // ---- phase 1: scan all nine columns; the hit masks go to this thread's slots in shared memory ----
-    // (slot = {mask, index of the candidate in bit 0}; highest set bit = earliest candidate).
-    // Software pipeline over the columns (fast path): while column p is scanned, the rows of column p + 1 are
-    // already requested (prefetch.global.L1: the first touch of a window comes from L2) and the cell_end
-    // entries of column p + 2 are in flight.
-    const int tid = threadIdx.x;
-    int nch = 0;
-    auto fast_range = [&](int e, int &j0, int &j1) {
-        j0 = __shfl_sync(0xffffffffu, e, k_lo - kmin + 1);
-        j1 = __shfl_sync(0xffffffffu, e, k_hi - kmin + 2);
-        if (!fluid || e < 0) { j0 = 0; j1 = 0; }  // e < 0 is warp-uniform (column outside the grid)
-    };
-    auto prefetch_rows = [&](int j0, int j1) {
-        if (j1 > j0) {
-            const int a = j0 & ~3;
-            prefetch_l1(S.sx + a); prefetch_l1(S.sy + a); prefetch_l1(S.sz + a); prefetch_l1(S.sw + a);
-            prefetch_l1(S.sx + j1 - 1); prefetch_l1(S.sy + j1 - 1); prefetch_l1(S.sz + j1 - 1); prefetch_l1(S.sw + j1 - 1);
-        }
-    };
-    int j0n = 0, j1n = 0, e_next = 0;
-    if (fast) {
-        fast_range(col_entry(dens10_column(P, 0)), j0n, j1n);
-        prefetch_rows(j0n, j1n);
-        e_next = col_entry(dens10_column(P, 1));
-    }
-    for (int p = 0; p < 9; ++p) {
-        int j0, j1;
-        if (fast) {
-            j0 = j0n; j1 = j1n;
-            if (p + 1 < 9) {
-                fast_range(e_next, j0n, j1n);
-                prefetch_rows(j0n, j1n);
-                if (p + 2 < 9) e_next = col_entry(dens10_column(P, p + 2));
-            }
-        } else {
-            col_range_slow(dens10_column(P, p), j0, j1);
-        }
-        if (j1 <= j0) continue;
-        const int a0 = j0 & ~3;  // quads are 16-byte aligned: up to 3 candidates below the range are scanned and dropped
-        for (int jb = a0; jb < j1; jb += 32) {
-            const int len = min(32, j1 - jb);
-            uint32_t m = scan_soa(P, S.sx, S.sy, S.sz, jb, len, pi.x, pi.y, pi.z);
-            if (jb < j0) m &= 0xffffffffu >> (32 - len + (j0 - jb));  // candidates jb .. j0 - 1 are the top bits
-            if ((uint32_t)(i - jb) < (uint32_t)len) m &= ~(1u << (len - 1 - (i - jb)));  // p_i != p_j
-            if (m == 0u) continue;
-            const int top = jb + len - 1;
-            if (nch < DENS10_SLOTS) {
-                s_m[nch][tid] = m;
-                s_top[nch][tid] = top;
-                ++nch;
-            } else {  // more non-empty chunks than slots (very dense state): evaluate this one right away
-                while (m) {
-                    int hb = 31 - __clz(m);
-                    m &= ~(1u << hb);
-                    const int j = top - hb;
-                    visit(j, make_float4(__ldg(S.sx + j), __ldg(S.sy + j), __ldg(S.sz + j), __ldg(S.sw + j)));
-                }
-            }
-        }
-    }
-    // ---- phase 2: ONE loop over the hits of all columns (a per-column loop costs the warp the sum over columns
-    // of the per-column maxima: 50 iterations at 18 active lanes; this one the maximum of the per-lane totals: 30
-    // at 30), reading the candidate from the SoA rows the scan has just pulled into L1, one candidate ahead ----
-    {
-        int k = 0, top = 0;
-        uint32_t m = 0u;
-        // every stored mask is non-empty, so ONE predicated refill keeps the loop free of inner branches
-        auto next = [&](int &j) -> bool {
-            if (m == 0u && k < nch) { m = s_m[k][tid]; top = s_top[k][tid]; ++k; }
-            const bool ok = m != 0u;
-            const int hb = 31 - __clz(m | 1u);
-            m &= ~(1u << hb);
-            j = ok ? top - hb : j;
-            return ok;
-        };
-        int j = min(i, P.n - 1);
-        bool have = next(j);
-        float4 pj = make_float4(__ldg(S.sx + j), __ldg(S.sy + j), __ldg(S.sz + j), __ldg(S.sw + j));
-        while (have) {
-            int jn = j;
-            const bool hn = next(jn);  // jn == j when the lane has no further hit
-            const float4 pn = make_float4(__ldg(S.sx + jn), __ldg(S.sy + jn), __ldg(S.sz + jn), __ldg(S.sw + jn));
-            visit(j, pj);
-            j = jn; pj = pn; have = hn;
-        }
-    }
-    if (!fluid) return;
-
-    if (cnt <= NBR_CAP) {
-        S.nbr_cnt[i] = cnt;
-        // pad the list to a multiple of LIST_PAD with the particle itself: the batched force pass then
-        // loads whole batches without per-entry predicates (a self pair contributes exactly zero)
-        for (int k = cnt; k % LIST_PAD; ++k) { S.nbr_list[widx] = i; widx += (uint32_t)S.npad; }
-    } else {
-        S.nbr_cnt[i] = NBR_OVERFLOW;
-    }
-    float rho = pi.w * P.w0;
-    rho = FASTW ? fmaf(den, P.k2_w, rho) : rho + den;
-    rho *= P.rho0;
-    float vol = mi.x / rho;  // m_j / rho_j with the UNCLAMPED density (viscosity)
-    if (P.dfsph) {  // DFSPH.py:39-47: plain density, no clamp, no EOS
-        reinterpret_cast<float *>(S.veld + i)[3] = rho;
-        S.aux[i] = make_float4(vol, 0.0f, mi.x, 0.0f);
-        return;
-    }
-    float rc = fmaxf(rho, P.rho0);
-    float p = tait_pressure(P, rc);
-    float dp = p / (rc * rc);
-    reinterpret_cast<float *>(S.veld + i)[3] = rc;
-    reinterpret_cast<float *>(S.misc + i)[1] = p;
-    S.aux[i] = make_float4(vol, dp, mi.x, 0.0f);
-    if (P.uniform_fluid) {
-        float4 vb = S.veld[i];
-        S.fpv[2 * (size_t)i] = make_float4(pi.x, pi.y, pi.z, vol);
-        S.fpv[2 * (size_t)i + 1] = make_float4(vb.x, vb.y, vb.z, dp);
-    }
-}
-
 // Fused force pass, general particle masses: 3 x 16 B gathered per neighbour.
 template <int B, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_force_general(DevParams P, DevArrays S) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
-    if (P.slab_on && S.grid_ids[i] >= P.C) return;
+    if (P.slab_on && i >= S.sd[SD_N_LIVE]) return;
     float4 mi = S.misc[i];
     uint32_t fl = __float_as_uint(mi.z);
     if (!(fl & FLAG_FLUID)) return;  // initialised by k_density_tma
@@ -1274,24 +1060,21 @@ __device__ __forceinline__ void force_pair_packed(const DevParams &P, const DevA
 #ifndef FORCE_THREADS
 #define FORCE_THREADS 128
 #endif
-#ifndef FORCE_PREFETCH
-#define FORCE_PREFETCH 1
-#endif
-// split_info / split_mode (slab mode): process only the particles inside (mode 0) or outside (mode 1)
-// the index ranges this rank sends to its neighbours (info[1..8) / info[9..4), see k_slab_info), so
-// that the halo exchange of the next step can start while the interior is still being computed.
+// split_mode (sharded steps): 1 = only the particles inside the index ranges this rank sends to its neighbours
+// (k_shard_info), 2 = only the others, 0 = all -- the halo exchange of the NEXT step starts as soon as the
+// boundary particles are final and overlaps the interior.
 static_assert(LIST_PAD % FORCE_BATCH == 0 && NBR_CAP % LIST_PAD == 0, "list padding must cover a force batch");
 template <int B, int THREADS, bool FUSE_ADVECT>
 __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevParams P, DevArrays S,
-                                                                            const int32_t *__restrict__ split_info,
                                                                             int split_mode) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
-    if (split_info) {
-        bool boundary = (i >= split_info[1] && i < split_info[8]) || (i >= split_info[9] && i < split_info[4]);
-        if ((split_mode == 0) != boundary) return;
+    if (split_mode) {
+        const int32_t *sd = S.sd;
+        bool boundary = (i >= sd[SD_SEND_L0] && i < sd[SD_SEND_L1]) || (i >= sd[SD_SEND_R0] && i < sd[SD_SEND_R1]);
+        if ((split_mode == 1) != boundary) return;
     }
-    if (P.slab_on && S.grid_ids[i] >= P.C) return;
+    if (P.slab_on && i >= S.sd[SD_N_LIVE]) return;
     float4 mi = S.misc[i];
     uint32_t fl = __float_as_uint(mi.z);
     if (!(fl & FLAG_FLUID)) return;
@@ -1309,41 +1092,11 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
         // 32-bit list slots (sph_create bounds NBR_CAP * npad below 2^32): one IADD + one IMAD.WIDE per load
         const uint32_t np = (uint32_t)S.npad;
         uint32_t slot = (uint32_t)i;
-#if FORCE_PREFETCH
-        // Two-deep software pipeline WITHOUT holding records in registers: while batch t is evaluated, the indices
-        // of batch t + 1 are already loaded and its records requested into L1 (CCTL.E.PF1), and the list rows of
-        // batch t + 2 are requested too -- the gathers of a batch then hit L1 instead of waiting ~300 cycles
-        // behind a dependent list load (v8 profile: 10 warps per issue stalled on long_scoreboard).
-        int jn[B];
-#pragma unroll
-        for (int u = 0; u < B; ++u) jn[u] = (cnt > 0) ? __ldg(S.nbr_list + (slot + (uint32_t)u * np)) : i;
-#pragma unroll
-        for (int u = 0; u < B; ++u) prefetch_l1(S.fpv + 2 * (size_t)jn[u]);
-        if (cnt > B) {
-#pragma unroll
-            for (int u = 0; u < B; ++u) prefetch_l1(S.nbr_list + (slot + (uint32_t)(B + u) * np));
-        }
-#endif
         for (int k0 = 0; k0 < cnt; k0 += B) {
             int j[B];  // the density pass padded the list to a multiple of LIST_PAD with i itself
             float4 pj[B], vj[B];
-#if FORCE_PREFETCH
-#pragma unroll
-            for (int u = 0; u < B; ++u) j[u] = jn[u];
-            if (k0 + B < cnt) {
-#pragma unroll
-                for (int u = 0; u < B; ++u) jn[u] = __ldg(S.nbr_list + (slot + (uint32_t)(B + u) * np));
-#pragma unroll
-                for (int u = 0; u < B; ++u) prefetch_l1(S.fpv + 2 * (size_t)jn[u]);
-                if (k0 + 2 * B < cnt) {
-#pragma unroll
-                    for (int u = 0; u < B; ++u) prefetch_l1(S.nbr_list + (slot + (uint32_t)(2 * B + u) * np));
-                }
-            }
-#else
 #pragma unroll
             for (int u = 0; u < B; ++u) j[u] = ldg_stream(S.nbr_list + (slot + (uint32_t)u * np));
-#endif
 #pragma unroll
             for (int u = 0; u < B; ++u) SPH_EMU_CHECK(k0 + u < NBR_CAP && j[u] >= 0 && j[u] < P.n);  // padded with i
 #pragma unroll
@@ -1405,7 +1158,7 @@ __global__ void k_advect_solids(DevParams P, DevArrays S) {
 __global__ void k_neighbor_stats(DevParams P, DevArrays S, int32_t *out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
-    if (P.slab_on && S.grid_ids[i] >= P.C) return;
+    if (P.slab_on && i >= S.sd[SD_N_LIVE]) return;
     uint32_t fl = __float_as_uint(S.misc[i].z);
     if (!(fl & FLAG_FLUID)) return;
     int c = S.nbr_cnt[i];

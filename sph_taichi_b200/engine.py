@@ -101,12 +101,16 @@ class Engine:
         self.params = params
         self._check(self.lib.sph_set_params(self.ctx, C.byref(params)), "sph_set_params")
 
-    def pack(self, tensors, n, n_solid, has_dynamic_solids):
+    def pack(self, tensors, n, n_solid, has_dynamic_solids, uniform_hint=None):
+        """uniform_hint = (uniform, fluid_m, fluid_mV) decided by the caller for the WHOLE scene (sharded runs: a
+        rank that starts without particles must still run the same kernels as its peers); None derives it here."""
         self._check(self.lib.sph_set_solid_count(self.ctx, int(n_solid), int(bool(has_dynamic_solids))),
                     "sph_set_solid_count")
         # uniform-fluid hint: all fluid particles share one m and one m_V (bitwise)
         uniform, fm, fmv = 0, 0.0, 0.0
-        if n > 0:
+        if uniform_hint is not None:
+            uniform, fm, fmv = int(bool(uniform_hint[0])), float(uniform_hint[1]), float(uniform_hint[2])
+        elif n > 0:
             fluid = tensors["material"][:n] == 1
             if bool(fluid.any().item()):
                 m, mv = tensors["m"][:n][fluid], tensors["m_V"][:n][fluid]

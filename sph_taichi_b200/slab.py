@@ -1,27 +1,21 @@
 """x-slab sharding of one WCSPH scene across the GPUs of a node (one process per GPU).
 
-The reference is single-device; this is the multi-GPU extension BASELINE.json asks for
-(SURVEY.md section 8e).  Design:
+The reference is single-device; this is the multi-GPU extension BASELINE.json asks for.
 
-* The grid is cut into slabs of whole x cell-layers, balanced by particle count (``plan_slabs``).
-  After the counting sort (x-major flattening, reference ``particle_system.py:292-294``) every
-  cell layer is ONE contiguous index range of the packed arrays.
-* Interaction radius = one cell, so each rank keeps 2 ghost layers per side: densities of the
-  first ghost layer are recomputed locally from the second, and a SINGLE exchange per step is
-  enough.  A step is
+* The grid is cut into slabs of whole x cell-layers, balanced by particle count (``plan_slabs``).  After the
+  counting sort (x-major flattening, reference ``particle_system.py:292-294``) every cell layer is ONE contiguous
+  index range of the packed arrays.
+* Interaction radius = one cell, so each rank keeps 2 ghost layers per side: densities of the first ghost layer are
+  recomputed locally from the second, and a SINGLE exchange per step is enough.
+* The whole sharded step lives in ``libsph_b200.so`` (``sph_shard_*``, include/sph_b200.h): live counts, slab
+  bounds, send / receive ranges and the record counts (in-band headers) are DEVICE state, the exchange is NCCL
+  point-to-point issued by the library on its own communicator, and classify + sort + pair passes + exchange
+  replay from one CUDA graph per step.  The host (this module) only builds the scene, hands the library its share
+  and launches graphs; it never waits on the device inside a step.  Cuts are re-balanced on the device every
+  ``rebalance_every`` steps.
 
-      exchange   : NCCL send/recv (one batched group) of the raw records of my outermost
-                   3 layers per side, straight out of / into the engine's packed arrays;
-      classify   : every record becomes owned / ghost / dropped from its position alone
-                   (``k_hash_count`` slab branch) -- migration needs no extra message;
-      sort, density (owned + ghosts), forces + integration (owned only).
-
-* The send ranges for step s+1 are known right after the sort of step s; they are all-gathered
-  while the pair kernels of step s run, so the host never waits on the device mid-step.
-
-The protocol (``SlabSimulation``) talks to a *backend* object; the CUDA engine backend is
-``EngineBackend``.  tests/test_slab_gloo.py drives the same protocol with a CPU backend over the
-gloo process group.
+``tests/test_slab_gloo.py`` runs the same library code on the CPU: the host-emulated build of the kernels
+(tests/emu/) with ``GlooTransport`` -- torch.distributed point-to-point over gloo -- in place of NCCL.
 """
 from __future__ import annotations
 
@@ -34,13 +28,17 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _lib
+
 GHOST_LAYERS = 2
-INFO_INTS = 12   # see include/sph_b200.h: sph_slab_step
-MIN_WIDTH_REBALANCE = GHOST_LAYERS + 3  # a slab must still contain its wide send range after giving a layer away
+SEND_LAYERS = GHOST_LAYERS + 2  # one more than the ghost band needs: a cut may move by a layer in any step
 RECORD_ARRAYS = 4  # posm, veld, x0id, misc (acc is recomputed every step and not exchanged)
+INFO_KEYS = ("n_live", "owned", "x_lo", "x_hi", "step", "own_begin", "own_end", "sendL_begin", "sendL_end",
+             "sendR_begin", "sendR_end", "recv_left", "recv_right", "n_sorted", "status")
+STATUS_OUT_OF_GRID, STATUS_HALO_CAPACITY, STATUS_SHARD_CAPACITY = 1, 4, 8
 
 
-def plan_slabs(layer_counts, world, min_width=GHOST_LAYERS + 1):
+def plan_slabs(layer_counts, world, min_width=SEND_LAYERS + 1):
     """Cut ``len(layer_counts)`` x cell-layers into ``world`` contiguous slabs with balanced
     particle counts; every slab at least ``min_width`` layers wide.  Returns [(lo, hi)] * world."""
     counts = np.asarray(layer_counts, dtype=np.int64)
@@ -66,13 +64,63 @@ def layer_of(x, h):
     return (np.asarray(x, dtype=np.float32)[:, 0] / np.float32(h)).astype(np.int32)
 
 
-class EngineBackend:
-    """CUDA engine behind the slab protocol."""
+def select_owned(arrays, h, lo, hi):
+    lay = layer_of(arrays["x"], h)
+    m = (lay >= lo) & (lay < hi)
+    return {k: v[m] for k, v in arrays.items()}, int(m.sum())
 
-    def __init__(self, cfg, n_max, device):
+
+class GlooTransport:
+    """SphTransport on torch.distributed point-to-point over HOST memory (TEST transport: the host-emulated
+    library keeps its buffers in host memory; the product path is NCCL inside the library)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.reqs = []
+        self.keep = []
+        self.send_tag, self.recv_tag = {}, {}
+
+        def view(ptr, nbytes):
+            buf = (C.c_uint8 * int(nbytes)).from_address(ptr)
+            self.keep.append(buf)
+            return torch.frombuffer(buf, dtype=torch.uint8)
+
+        def group_start(_user):
+            return 0
+
+        def group_end(_user, _stream):
+            for r in self.reqs:
+                r.wait()
+            self.reqs.clear()
+            self.keep.clear()
+            return 0
+
+        def send(_user, ptr, nbytes, peer, _stream):
+            tag = self.send_tag.get(peer, 0)
+            self.send_tag[peer] = tag + 1
+            self.reqs.append(dist.isend(view(ptr, nbytes), peer, group=self.group, tag=tag % 30000))
+            return 0
+
+        def recv(_user, ptr, nbytes, peer, _stream):
+            tag = self.recv_tag.get(peer, 0)
+            self.recv_tag[peer] = tag + 1
+            self.reqs.append(dist.irecv(view(ptr, nbytes), peer, group=self.group, tag=tag % 30000))
+            return 0
+
+        self._cb = (_lib.TRANSPORT_GROUP_START(group_start), _lib.TRANSPORT_GROUP_END(group_end),
+                    _lib.TRANSPORT_SEND(send), _lib.TRANSPORT_RECV(recv))
+        self.struct = _lib.SphTransport(None, *self._cb)
+
+
+class ShardedSimulation:
+    """This rank's share of a sharded scene: a CUDA engine in slab mode + the library's halo exchange."""
+
+    def __init__(self, cfg, mine, n_mine, slabs, rank, world, device, n_cap, halo_cap, uniform_hint, group=None,
+                 rebalance_every=8, transport=None):
         from . import engine as _engine
-        self.cfg = cfg
+        self.cfg, self.rank, self.world, self.group = cfg, rank, world, group
         self.device = torch.device(device)
+        self.slabs0 = [tuple(int(v) for v in s_) for s_ in slabs]
         ds = np.array(cfg.get_cfg("domainEnd"), dtype=np.float64) - np.array(cfg.get_cfg("domainStart"))
         radius = cfg.get_cfg("particleRadius")
         self.h = radius * 4.0
@@ -80,19 +128,41 @@ class EngineBackend:
         params = _engine.make_params(3, self.grid_num, radius, cfg.get_cfg("density0"), cfg.get_cfg("stiffness"),
                                      cfg.get_cfg("exponent"), cfg.get_cfg("timeStepSize"), cfg.get_cfg("gravitation"), ds)
         self.m_V0 = float(np.float32(0.8 * (2 * radius) ** 3))
-        self.n_max = int(n_max)
-        self.eng = _engine.Engine(params, n_max=self.n_max, n_solid=0, n_bodies=0, device=self.device)
-        self.info_dev = torch.zeros(INFO_INTS, dtype=torch.int32, device=self.device)
-        self._floats = self.eng.workspace.view(torch.uint8)
+        self.n_cap, self.halo_cap = int(n_cap), int(halo_cap)
+        self.eng = _engine.Engine(params, n_max=self.n_cap, n_solid=0, n_bodies=0, device=self.device)
+        e = self.eng
+        self._load(mine, n_mine, uniform_hint)
+        # ---- transport: NCCL inside the library (its own communicator), or a caller-supplied one (tests) ----
+        if transport is not None:
+            self._transport = transport
+            e._check(e.lib.sph_comm_set_transport(e.ctx, C.byref(transport.struct), rank, world), "sph_comm_set_transport")
+        elif world > 1:
+            ident = [None]
+            if rank == 0:
+                buf = C.create_string_buffer(128)
+                rc = e.lib.sph_comm_unique_id(buf)
+                if rc:
+                    raise RuntimeError(f"sph_comm_unique_id failed ({rc}): {e.lib.sph_last_error(None).decode()}")
+                ident = [buf.raw]
+            dist.broadcast_object_list(ident, src=0, group=group)
+            e._check(e.lib.sph_comm_init_nccl(e.ctx, ident[0], rank, world), "sph_comm_init_nccl")
+        else:
+            e._check(e.lib.sph_comm_set_transport(e.ctx, None, 0, 1), "sph_comm_set_transport")
+        lo, hi = self.slabs0[rank]
+        e._check(e.lib.sph_shard_configure(e.ctx, lo, hi, GHOST_LAYERS, self.halo_cap, int(rebalance_every)),
+                 "sph_shard_configure")
+        e._check(e.lib.sph_shard_begin(e.ctx, e._stream()), "sph_shard_begin")
+        self.steps_done = 0
 
-    def load(self, arrays):
+    def _load(self, arrays, n, uniform_hint):
         """Pack this rank's initial particles (numpy arrays in the reference's field layout)."""
-        n = arrays["x"].shape[0]
         dev = self.device
 
         def t(a, dt):
             return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
 
+        if int((np.asarray(arrays["material"]) != 1).sum()) != 0:
+            raise NotImplementedError("x-slab sharding supports fluid-only scenes (SURVEY.md section 8e)")
         dens = t(arrays["density"], np.float32)
         f = {
             "object_id": t(arrays["object_id"], np.int32), "x": t(arrays["x"], np.float32),
@@ -103,283 +173,88 @@ class EngineBackend:
             "is_dynamic": t(arrays["is_dynamic"], np.int32), "color": t(arrays["color"], np.int32),
             "grid_ids": None, "solid_id": None,
         }
-        if int((f["material"] != 1).sum().item()) != 0:
-            raise NotImplementedError("x-slab sharding supports fluid-only scenes (SURVEY.md section 8e)")
-        self.eng.pack(f, n, 0, False)
-        self._keep = f
-        torch.cuda.synchronize(self.device)
-        self._keep = None
+        self.eng.pack(f, n, 0, False, uniform_hint=uniform_hint)
+        self.synchronize()  # the temporaries above may be freed now
 
-    def configure(self, lo, hi, ghost_layers):
-        self.eng._check(self.eng.lib.sph_slab_configure(self.eng.ctx, int(lo), int(hi), int(ghost_layers)),
-                        "sph_slab_configure")
+    # ---- stepping --------------------------------------------------------------------------------------
+    def step(self, n=1):
+        e = self.eng
+        e._check(e.lib.sph_shard_step(e.ctx, int(n), e._stream()), "sph_shard_step")
+        self.steps_done += int(n)
+
+    def profile_step(self):
+        """ONE un-graphed step with CUDA events between the stages (synchronises)."""
+        e = self.eng
+        buf = (C.c_float * 4)()
+        e._check(e.lib.sph_shard_profile_step(e.ctx, buf, e._stream()), "sph_shard_profile_step")
+        self.steps_done += 1
+        return {"sort_ms": buf[0], "density_ms": buf[1], "boundary_force_pack_ms": buf[2], "interior_force_or_exchange_ms": buf[3]}
+
+    def info(self):
+        """The device-resident step state (synchronising read); raises on a capacity / out-of-grid flag."""
+        e = self.eng
+        out = (C.c_int32 * 16)()
+        sent = C.c_uint64(0)
+        e._check(e.lib.sph_shard_info(e.ctx, out, C.byref(sent), e._stream()), "sph_shard_info")
+        d = {k: int(out[i]) for i, k in enumerate(INFO_KEYS)}
+        d["halo_records_sent"] = int(sent.value)
+        st = d["status"]
+        if st & STATUS_OUT_OF_GRID:
+            raise RuntimeError("a particle left the grid (NaN or outside [0, domain))")
+        if st & (STATUS_HALO_CAPACITY | STATUS_SHARD_CAPACITY):
+            raise RuntimeError(f"rank {self.rank}: slab capacity exceeded (status {st}: halo_capacity {self.halo_cap}, "
+                               f"capacity {self.n_cap}, live {d['n_live']}); raise capacity_factor")
+        return d
+
+    @property
+    def slab(self):
+        d = self.info()
+        return d["x_lo"], d["x_hi"]
+
+    @property
+    def halo_bytes(self):
+        return 16 * RECORD_ARRAYS * self.info()["halo_records_sent"]
+
+    def owned_count(self):
+        return self.info()["owned"]
 
     def record_views(self):
-        """The 4 exchanged packed arrays as [n_max, 4] float32 views of the engine workspace."""
+        """The 4 exchanged packed arrays as [n_cap, 4] float32 views of the engine workspace (current buffer set)."""
         off = (C.c_uint64 * 5)()
-        self.eng._check(self.eng.lib.sph_state_offsets(self.eng.ctx, off), "sph_state_offsets")
-        key = int(off[0])
-        cache = self.__dict__.setdefault("_view_cache", {})
-        if key not in cache:  # two entries: the ping-pong buffer sets
-            base = self.eng._ws_ptr - self.eng.workspace.data_ptr()
-            views = []
-            for k in range(RECORD_ARRAYS):
-                b0 = base + int(off[k])
-                views.append(self.eng.workspace[b0:b0 + self.n_max * 16].view(torch.float32).view(self.n_max, 4))
-            cache[key] = views
-        return cache[key]
-
-    def sort(self, n_local, n_recv):
         e = self.eng
-        e._check(e.lib.sph_slab_set_counts(e.ctx, int(n_local), int(n_recv)), "sph_slab_set_counts")
-        e._check(e.lib.sph_slab_step(e.ctx, self.info_dev.data_ptr(), 1, e._stream()), "sph_slab_step")
-        return self.info_dev
+        e._check(e.lib.sph_state_offsets(e.ctx, off), "sph_state_offsets")
+        base = e._ws_ptr - e.workspace.data_ptr()
+        views = []
+        for k in range(RECORD_ARRAYS):
+            b0 = base + int(off[k])
+            views.append(e.workspace[b0:b0 + self.n_cap * 16].view(torch.float32).view(self.n_cap, 4))
+        return views
 
-    def compute(self):
-        e = self.eng
-        e._check(e.lib.sph_slab_compute(e.ctx, e._stream()), "sph_slab_compute")
-
-    def compute_phase(self, phase):
-        """phase 0: density + forces of the send ranges; phase 1: forces of the interior."""
-        e = self.eng
-        e._check(e.lib.sph_slab_compute_split(e.ctx, self.info_dev.data_ptr(), int(phase), e._stream()),
-                 "sph_slab_compute_split")
-
-    def owned_state(self, info_row):
-        """(x, v, x_0) of the owned particles as numpy arrays."""
+    def owned_tensors(self):
+        """(x, v, x_0) of the owned particles as device tensors [owned, 3]."""
+        d = self.info()
         v = self.record_views()
-        b, e_ = int(info_row[1]), int(info_row[4])
-        posm, veld, x0id = v[0][b:e_].cpu().numpy(), v[1][b:e_].cpu().numpy(), v[2][b:e_].cpu().numpy()
-        misc = v[3][b:e_].cpu().numpy().view(np.uint32)
-        ghost = (misc[:, 2] & 4) != 0
+        b, e_ = d["own_begin"], d["own_end"]
+        ghost = (v[3][b:e_, 2].contiguous().view(torch.int32) & 4) != 0
         keep = ~ghost
-        return posm[keep, :3], veld[keep, :3], x0id[keep, :3]
+        return v[0][b:e_, :3][keep], v[1][b:e_, :3][keep], v[2][b:e_, :3][keep]
+
+    def owned_state(self):
+        x, v, x0 = self.owned_tensors()
+        return x.cpu().numpy(), v.cpu().numpy(), x0.cpu().numpy()
 
     def launch_count(self):
         return self.eng.launch_count()
 
-    def pair_times(self, enable=True):
-        """Switch the per-kernel CUDA-event timing on/off; returns (density_ms, force_ms) of the last timed step."""
-        buf = (C.c_float * 2)(0.0, 0.0)
-        self.eng._check(self.eng.lib.sph_slab_pair_times(self.eng.ctx, int(enable), buf), "sph_slab_pair_times")
-        return float(buf[0]), float(buf[1])
-
     def synchronize(self):
-        torch.cuda.synchronize(self.device)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
 
 
-class SlabSimulation:
-    """The sharded step protocol; see the module docstring."""
-
-    def __init__(self, backend, slabs, rank, world, group=None, rebalance_every=8):
-        self.b = backend
-        self.slabs = [tuple(int(v) for v in s_) for s_ in slabs]
-        self.rebalance_every = int(rebalance_every)  # 0 disables; at most one layer per cut and event
-        self.overlap = True   # post the next exchange while the interior particles are still computed
-        self._exch = None
-        self.rebalances = 0
-        self.rank, self.world = rank, world
-        self.group = group
-        self.lo, self.hi = slabs[rank]
-        self.info_all = None  # host copy of every rank's info row
-        self._pending = None
-        self.halo_bytes = 0
-        self.steps_done = 0
-
-    # -- helpers ---------------------------------------------------------------------------
-    def _gather_info(self, info_dev):
-        """all_gather the info rows; the host copy is awaited lazily at the next step.  On the GPU
-        the collective and the D2H copy run on a side stream so the pair kernels start immediately."""
-        if not info_dev.is_cuda:
-            if self.world == 1:
-                gathered = info_dev.clone().view(1, INFO_INTS)
-            else:
-                gathered = torch.empty((self.world, INFO_INTS), dtype=info_dev.dtype)
-                dist.all_gather_into_tensor(gathered.view(-1), info_dev, group=self.group)
-            self._pending = (gathered, None, None)
-            return
-        if not hasattr(self, "_pinned"):
-            self._pinned = [torch.empty((self.world, INFO_INTS), dtype=info_dev.dtype).pin_memory() for _ in range(2)]
-            self._gathered = [torch.empty((self.world, INFO_INTS), dtype=info_dev.dtype, device=info_dev.device) for _ in range(2)]
-            self._events = [torch.cuda.Event() for _ in range(2)]
-            self._side = torch.cuda.Stream(device=info_dev.device)
-            self._flip = 0
-        self._flip ^= 1
-        host, ev, gathered = self._pinned[self._flip], self._events[self._flip], self._gathered[self._flip]
-        main = torch.cuda.current_stream(info_dev.device)
-        self._side.wait_stream(main)  # the info kernel has run
-        with torch.cuda.stream(self._side):
-            if self.world == 1:
-                gathered.view(-1).copy_(info_dev)
-            else:
-                dist.all_gather_into_tensor(gathered.view(-1), info_dev, group=self.group)
-            host.copy_(gathered, non_blocking=True)
-            ev.record(self._side)
-        self._pending = (host, ev, gathered)
-
-    def _await_info(self):
-        host, ev, _ = self._pending
-        if ev is not None:
-            ev.synchronize()
-        self.info_all = host.numpy().copy()
-        st = int(self.info_all[:, 7].max())
-        if st & 1:
-            raise RuntimeError("a particle left the grid (NaN or outside [0, domain))")
-
-    def initialize(self, n_initial):
-        self.b.configure(self.lo, self.hi, GHOST_LAYERS)
-        info = self.b.sort(n_initial, 0)
-        self._gather_info(info)
-
-    # -- one sharded step ----------------------------------------------------------------------
-    def _post_exchange(self, after_event=None):
-        """Decide re-balancing, derive the send / receive ranges from the freshly gathered info rows and
-        post ONE batched NCCL send/recv group.  On CUDA the group is issued on a communication stream that
-        waits only for ``after_event`` (the boundary particles are final), so it overlaps whatever the
-        main stream does next.  Returns the pending-exchange record consumed by ``step``."""
-        me = self.info_all[self.rank]
-        n_live = int(me[0])
-        left, right = self.rank - 1, self.rank + 1
-        moves = self._plan_rebalance()  # moves[b] in {-1, 0, +1}: shift of the cut between ranks b-1 and b
-        wide_l = left >= 0 and moves[self.rank] != 0
-        wide_r = right < self.world and moves[right] != 0
-
-        def right_range(row, wide):   # what a rank sends to its RIGHT neighbour
-            return (int(row[9]) if wide else int(row[3])), int(row[4])
-
-        def left_range(row, wide):    # what a rank sends to its LEFT neighbour
-            return int(row[1]), (int(row[8]) if wide else int(row[2]))
-
-        n_from_left = 0
-        if left >= 0:
-            a_, b_ = right_range(self.info_all[left], wide_l)
-            n_from_left = b_ - a_
-        n_from_right = 0
-        if right < self.world:
-            a_, b_ = left_range(self.info_all[right], wide_r)
-            n_from_right = b_ - a_
-        sl0, sl1 = left_range(me, wide_l)
-        sr0, sr1 = right_range(me, wide_r)
-        if n_live + n_from_left + n_from_right > self.b.n_max:
-            raise RuntimeError(f"rank {self.rank}: slab capacity exceeded ({n_live}+{n_from_left}+{n_from_right} > "
-                               f"{self.b.n_max}); raise capacity_factor")
-        views = self.b.record_views()
-        ops = []
-        a0 = n_live
-        a1 = n_live + n_from_left
-        for arr in views:
-            if left >= 0:
-                if sl1 > sl0:
-                    ops.append(dist.P2POp(dist.isend, arr[sl0:sl1], left, self.group))
-                if n_from_left:
-                    ops.append(dist.P2POp(dist.irecv, arr[a0:a0 + n_from_left], left, self.group))
-            if right < self.world:
-                if sr1 > sr0:
-                    ops.append(dist.P2POp(dist.isend, arr[sr0:sr1], right, self.group))
-                if n_from_right:
-                    ops.append(dist.P2POp(dist.irecv, arr[a1:a1 + n_from_right], right, self.group))
-        reqs, comm = [], None
-        if ops:
-            if views[0].is_cuda:
-                if not hasattr(self, "_comm"):
-                    self._comm = torch.cuda.Stream(device=views[0].device)
-                comm = self._comm
-                main = torch.cuda.current_stream(views[0].device)
-                if after_event is not None:
-                    comm.wait_event(after_event)
-                else:
-                    comm.wait_stream(main)
-                with torch.cuda.stream(comm):
-                    reqs = dist.batch_isend_irecv(ops)
-                    for req in reqs:
-                        req.wait()  # the comm stream (not the host, not the main stream) waits for NCCL
-            else:
-                reqs = dist.batch_isend_irecv(ops)
-        self.halo_bytes += 16 * RECORD_ARRAYS * (n_from_left + n_from_right)
-        return {"n_live": n_live, "n_recv": n_from_left + n_from_right, "moves": moves, "reqs": reqs, "comm": comm}
-
-    def step(self):
-        if self._exch is None:  # nothing pre-posted: first step, or overlap switched off
-            self._await_info()
-            self._exch = self._post_exchange(None)
-        ex, self._exch = self._exch, None
-        if ex["comm"] is not None:
-            torch.cuda.current_stream().wait_stream(ex["comm"])  # received records are in place
-        else:
-            for req in ex["reqs"]:
-                req.wait()
-        if any(ex["moves"]):
-            cuts = [s_[0] for s_ in self.slabs] + [self.slabs[-1][1]]
-            cuts = [c + m for c, m in zip(cuts, ex["moves"] + [0])]
-            self.slabs = [(cuts[r], cuts[r + 1]) for r in range(self.world)]
-            self.lo, self.hi = self.slabs[self.rank]
-            self.b.configure(self.lo, self.hi, GHOST_LAYERS)
-            self.rebalances += 1
-        info = self.b.sort(ex["n_live"], ex["n_recv"])
-        self._gather_info(info)
-        self.steps_done += 1
-        if self.overlap and self.world > 1 and hasattr(self.b, "compute_phase"):
-            # density + the particles I am about to send, then the exchange of the NEXT step goes out on
-            # the communication stream while the interior particles are still being processed
-            prof = os.environ.get("SPH_SLAB_PROF")
-            self.b.compute_phase(0)
-            ev = torch.cuda.Event(enable_timing=bool(prof))
-            ev.record()
-            self.b.compute_phase(1)  # queued first: the host-side cost of posting NCCL must not idle the GPU
-            self._await_info()       # host waits for this step's sort only; the device is busy
-            self._exch = self._post_exchange(ev)
-            if prof and self._exch["comm"] is not None:
-                e_comm = torch.cuda.Event(enable_timing=True)
-                e_comm.record(self._exch["comm"])
-                e_p1 = torch.cuda.Event(enable_timing=True)
-                e_p1.record()
-                self.__dict__.setdefault("_ovl", []).append((ev, e_comm, e_p1))
-                if self.steps_done % 50 == 0:
-                    torch.cuda.synchronize()
-                    rows = self._ovl[-40:]
-                    print(f"[rank {self.rank}] after phase 0: exchange done at +%.0f us, interior force done at +%.0f us" % (
-                        sum(a.elapsed_time(b) for a, b, _ in rows) / len(rows) * 1e3,
-                        sum(a.elapsed_time(c) for a, _, c in rows) / len(rows) * 1e3), flush=True)
-                    self._ovl.clear()
-        else:
-            self.b.compute()
-
-    def _plan_rebalance(self):
-        """Every rank derives the same decision from the all-gathered owned counts: a cut moves one layer
-        toward the heavier side when the difference exceeds ~1.2 layers' worth of particles."""
-        moves = [0] * self.world  # moves[0] is the domain edge and never moves
-        if not self.rebalance_every or self.world == 1 or (self.steps_done % self.rebalance_every) != 0:
-            return moves
-        owned = [int(v) for v in self.info_all[:, 6]]
-        width = [hi - lo for lo, hi in self.slabs]
-        for b in range(1, self.world):
-            l_, r_ = b - 1, b
-            if owned[l_] - owned[r_] > 1.2 * owned[l_] / max(width[l_], 1) and width[l_] > MIN_WIDTH_REBALANCE:
-                moves[b] = -1   # the left rank gives its last layer to the right rank
-                width[l_] -= 1; width[r_] += 1
-            elif owned[r_] - owned[l_] > 1.2 * owned[r_] / max(width[r_], 1) and width[r_] > MIN_WIDTH_REBALANCE:
-                moves[b] = +1
-                width[l_] += 1; width[r_] -= 1
-        return moves
-
-    def owned_state(self):
-        self._await_info()
-        return self.b.owned_state(self.info_all[self.rank])
-
-    def owned_count(self):
-        self._await_info()
-        return int(self.info_all[self.rank][6])
-
-
-def select_owned(arrays, h, lo, hi):
-    lay = layer_of(arrays["x"], h)
-    m = (lay >= lo) & (lay < hi)
-    return {k: v[m] for k, v in arrays.items()}, int(m.sum())
-
-
-def build_sharded(scene_dict, rank, world, device, group=None, capacity_factor=1.35):
-    """Assemble the scene on every rank, plan the slabs from the initial layer histogram and load
-    this rank's share into a CUDA engine.  Returns (SlabSimulation, n_total)."""
+def build_sharded(scene_dict, rank, world, device, group=None, capacity_factor=1.35, rebalance_every=8, slabs=None,
+                  transport=None):
+    """Assemble the scene on every rank, plan the slabs from the initial layer histogram and load this rank's
+    share into a CUDA engine.  Returns (ShardedSimulation, n_total)."""
     from .config_builder import SimConfig
     from .scene import assemble_particles
 
@@ -391,18 +266,72 @@ def build_sharded(scene_dict, rank, world, device, group=None, capacity_factor=1
     gx = int(np.ceil(ds / h).astype(int)[0])
     lay = layer_of(arrays["x"], h)
     hist = np.bincount(lay, minlength=gx)[:gx]
-    slabs = plan_slabs(hist, world)
+    if slabs is None:
+        slabs = plan_slabs(hist, world)
     lo, hi = slabs[rank]
     mine, n_mine = select_owned(arrays, h, lo, hi)
-    # live ghosts (2 layers per side) + the records received each step (3 layers per side); the
-    # fullest layer bounds every layer the front may reach later
-    ghost_est = 2 * (2 * GHOST_LAYERS + 1) * int(hist.max())
-    n_max = int((n_mine + ghost_est) * capacity_factor) + 1024
-    backend = EngineBackend(cfg, n_max, device)
-    backend.load(mine)
-    sim = SlabSimulation(backend, slabs, rank, world, group)
-    sim.initialize(n_mine)
+    # one decision for the whole scene (a rank may start empty): all fluid particles share m and m_V?
+    fluid = arrays["material"] == 1
+    dens = arrays["density"][fluid].astype(np.float32)
+    m_V0 = np.float32(0.8 * (2 * radius) ** 3)
+    uniform = bool(fluid.all() and dens.size and (dens == dens[0]).all())
+    hint = (uniform, float(np.float32(m_V0 * dens[0])) if dens.size else 0.0, float(m_V0))
+    # the fullest layer bounds every layer the front may reach later: SEND_LAYERS of them per side and direction
+    halo_cap = int(SEND_LAYERS * int(hist.max()) * capacity_factor) + 1024
+    ghost_est = 2 * GHOST_LAYERS * int(hist.max())
+    n_cap = int((n_mine + ghost_est) * capacity_factor) + 4 * halo_cap + 1024  # live + trash + 2 receive regions
+    sim = ShardedSimulation(cfg, mine, n_mine, slabs, rank, world, device, n_cap, halo_cap, hint, group=group,
+                            rebalance_every=rebalance_every, transport=transport)
     return sim, counts["total"]
+
+
+# -----------------------------------------------------------------------------------------------
+# sharded state against the single-GPU engine (bench.py --gpus N parity_check, tools/check_slab_parity.py)
+# -----------------------------------------------------------------------------------------------
+def _lexsort_rows(x0):
+    """Permutation sorting the rows of a [n, 3] tensor lexicographically (x, then y, then z) on its device."""
+    order = torch.arange(x0.shape[0], device=x0.device)
+    for col in (2, 1, 0):
+        _, idx = torch.sort(x0[order, col], stable=True)
+        order = order[idx]
+    return order
+
+
+def gather_owned(sim, dst=0):
+    """All ranks' owned (x, v, x_0) gathered on rank `dst` as device tensors (None elsewhere)."""
+    x, v, x0 = sim.owned_tensors()
+    rec = torch.cat([x, v, x0], dim=1).contiguous()
+    if sim.world == 1:
+        return rec[:, 0:3], rec[:, 3:6], rec[:, 6:9]
+    n = torch.tensor([rec.shape[0]], device=rec.device, dtype=torch.int64)
+    counts = [torch.zeros_like(n) for _ in range(sim.world)]
+    dist.all_gather(counts, n, group=sim.group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(counts)
+    pad = torch.zeros((cap, 9), device=rec.device, dtype=rec.dtype)
+    pad[:rec.shape[0]] = rec
+    bufs = [torch.empty_like(pad) for _ in range(sim.world)] if sim.rank == dst else None
+    dist.gather(pad, bufs, dst=dst, group=sim.group)
+    if sim.rank != dst:
+        return None
+    full = torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    return full[:, 0:3], full[:, 3:6], full[:, 6:9]
+
+
+def compare_with_single(gathered, ps, d):
+    """Rank 0: the gathered sharded state against a ParticleSystem that ran the same steps on ONE GPU."""
+    X, V, X0 = gathered
+    ps._pull()
+    rx, rv, rx0 = ps._t["x"], ps._t["v"], ps._t["x_0"]
+    same = tuple(X0.shape) == tuple(rx0.shape)
+    dx = dv = float("inf")
+    if same:
+        ks, kr = _lexsort_rows(X0), _lexsort_rows(rx0)
+        same = bool(torch.equal(X0[ks], rx0[kr]))
+        if same:
+            dx = float((X[ks] - rx[kr]).abs().max().item() / d)
+            dv = float((V[ks] - rv[kr]).abs().max().item())
+    return {"same_particle_set": bool(same), "max_dx_over_d": dx, "max_dv": dv, "particles": int(X0.shape[0])}
 
 
 # -----------------------------------------------------------------------------------------------
@@ -410,6 +339,7 @@ def build_sharded(scene_dict, rank, world, device, group=None, capacity_factor=1
 # -----------------------------------------------------------------------------------------------
 def bench_main(args):
     import bench as _bench  # the repo-root module: shared helpers
+    from . import ParticleSystem, SimConfig
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -421,73 +351,104 @@ def bench_main(args):
     os.environ.setdefault("MASTER_PORT", "29511")
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
-    # the halo exchange must get SMs while the interior force pass is running
-    os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     name, sc = _bench.scene_for(world, args.scene)
+    d = 2.0 * sc["Configuration"]["particleRadius"]
     sim, n_total = build_sharded(sc, rank, world, dev)
     K, W = args.steps, args.warmup
-    for _ in range(W):
-        sim.step()
-    sim.b.synchronize()
+
+    # ---- parity_check + the same-run single-GPU time: rank 0 steps the SAME scene on one GPU ----
+    P = int(os.environ.get("SPH_BENCH_PARITY_STEPS", "20"))
+    sim.step(P)
+    gathered = gather_owned(sim)
+    parity, strong = None, None
+    if rank == 0:
+        ps = ParticleSystem(SimConfig(sc), device=dev)
+        solver = ps.build_solver()
+        solver.initialize()
+        solver.step(P)
+        parity = dict(compare_with_single(gathered, ps, d), steps=P, against="the single-GPU engine on rank 0, same scene, "
+                      "particles matched by x_0")
+        parity["ok"] = bool(parity["same_particle_set"] and parity["max_dx_over_d"] < 1e-3)
+        K1 = max(3, min(K, 20))
+        solver.step(3)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        solver.step(K1)
+        b.record()
+        torch.cuda.synchronize()
+        strong = {"t1_ms": a.elapsed_time(b) / K1, "t1_steps": K1,
+                  "note": "t1: the whole scene on rank 0's GPU alone (other ranks idle), same run, same scene, "
+                          "CUDA-graph steps right after the parity steps"}
+        del solver, ps, gathered
+        torch.cuda.empty_cache()
+    flag = torch.tensor([1 if (parity is None or parity["ok"]) else 0], device=dev)
+    dist.broadcast(flag, src=0)
+    if not bool(flag.item()):
+        if rank == 0:
+            print(json.dumps({"error": "parity_check failed", "parity_check": parity}))
+        dist.destroy_process_group()
+        return 3
+
+    sim.step(max(W - P, 3))
+    sim.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
     sampler = _bench.ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    halo0, launches0 = sim.halo_bytes, sim.b.launch_count()
+    info0, launches0 = sim.info(), sim.launch_count()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
     torch.cuda.synchronize()
     a.record()
-    for _ in range(K):
-        sim.step()
+    sim.step(K)
     b.record()
     torch.cuda.synchronize()
     dist.barrier()
     ms = torch.tensor([a.elapsed_time(b)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    owned = torch.tensor([sim.owned_count(), sim.halo_bytes - halo0, sim.b.launch_count() - launches0], device=dev,
-                         dtype=torch.float64)
+    info1 = sim.info()
+    owned = torch.tensor([info1["owned"], 64 * (info1["halo_records_sent"] - info0["halo_records_sent"]),
+                          sim.launch_count() - launches0], device=dev, dtype=torch.float64)
     tot = owned.clone()
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     mx = owned.clone()
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler else None
+    slabs = [None] * world
+    dist.all_gather_object(slabs, [info1["x_lo"], info1["x_hi"]])
 
-    # ---- force-kernel roofline on every rank (CUDA events around the launch, 10 extra steps) ----
-    sim.overlap = False  # the per-kernel timer brackets the un-split launches
-    sim.b.pair_times(True)
-    fsum = dsum = 0.0
-    for _ in range(10):
-        sim.step()
-        d_ms, f_ms = sim.b.pair_times(True)
-        dsum += d_ms / 10
-        fsum += f_ms / 10
-    sim.b.pair_times(False)
-    owned_now = sim.owned_count()
+    # ---- per-kernel times on every rank: CUDA events between the stages of un-graphed steps ----
+    acc = {}
+    R = 10
+    for _ in range(R):
+        for k_, v_ in sim.profile_step().items():
+            acc[k_] = acc.get(k_, 0.0) + v_ / R
+    live_now = sim.info()
     peak, peak_src = _bench.measured_hbm_peak()
-    roof = torch.tensor([fsum, dsum, float(owned_now)], device=dev, dtype=torch.float64)
+    roof = torch.tensor([acc["density_ms"], acc["boundary_force_pack_ms"] + acc["interior_force_or_exchange_ms"],
+                         float(live_now["n_live"]), float(live_now["owned"]), acc["sort_ms"]], device=dev, dtype=torch.float64)
     roof_max = roof.clone()
     dist.all_reduce(roof_max, op=dist.ReduceOp.MAX)
 
     # ---- e2e: every step, H2D of the live records' {x, m_V} and {v, rho} words from pinned host
     # memory, the sharded step, and D2H of the same words (what a host-side consumer reads) ----
     Ke = max(3, min(K, 50))
-    cap = sim.b.n_max
+    cap = sim.n_cap
     h_pos = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
     h_vel = torch.empty((cap, 4), dtype=torch.float32).pin_memory()
 
     def pull():
-        sim._await_info()
-        n_live = int(sim.info_all[rank][0])
-        v = sim.b.record_views()
+        n_live = sim.info()["n_live"]
+        v = sim.record_views()
         h_pos[:n_live].copy_(v[0][:n_live], non_blocking=True)
         h_vel[:n_live].copy_(v[1][:n_live], non_blocking=True)
         return n_live
 
     def push(n_live):
-        v = sim.b.record_views()
+        v = sim.record_views()
         v[0][:n_live].copy_(h_pos[:n_live], non_blocking=True)
         v[1][:n_live].copy_(h_vel[:n_live], non_blocking=True)
 
@@ -511,16 +472,34 @@ def bench_main(args):
         t_ms = float(ms.item())
         val = K / (t_ms * 1e-3)
         halo_per_step = float(tot[1].item()) / K
+        strong.update(tN_ms=t_ms / K, speedup=strong["t1_ms"] / (t_ms / K), n_gpus=world)
+        d_ms, f_ms = float(roof_max[0].item()), float(roof_max[1].item())
+        kernels = []
+        for kind, lms, n_part in (("density", d_ms, float(roof_max[2].item())), ("force", f_ms, float(roof_max[3].item()))):
+            ach = _bench.ALGO_BYTES[kind] * n_part / (lms * 1e-3) / 1e9
+            kernels.append({"kernel": _bench.KERNEL_NAME[kind] + ", slowest rank", "bound": "hbm", "achieved": ach, "peak": peak,
+                            "unit": "GB/s", "frac": ach / peak, "traffic": None, "avg_launch_ms": lms,
+                            "particles_this_rank": int(n_part),
+                            "algorithmic_bytes_per_particle": _bench.ALGO_BYTES[kind]})
+        kernels.sort(key=lambda e_: -e_["avg_launch_ms"])
+        roofline = dict(kernels[0])
+        roofline.update(peak_source=peak_src, kernels=kernels, sort_ms_slowest_rank=float(roof_max[4].item()),
+                        note="per GPU, slowest rank; CUDA events between the stages of un-graphed sharded steps (10 steps); "
+                             "density runs over owned + ghost particles, forces over owned; the force figure includes the "
+                             "boundary pass, the pack kernel and max(interior pass, halo exchange); the pair kernels are "
+                             "fp32-issue / LSU bound, not HBM bound (DESIGN.md section 5)")
         line = {
             "metric": _bench.METRIC, "value": val * n_total / 1e6, "unit": _bench.UNIT, "steps_per_s": val,
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "particles": n_total, "solver": "WCSPH", "dt": sc["Configuration"]["timeStepSize"],
-                       "parallelism": f"x-slab x{world}, 2 ghost layers, 1 NCCL send/recv group per step, overlapped with the "
-                                      "interior force pass; cuts re-balanced every 8 steps",
-                       "slabs": [list(map(int, s)) for s in sim.slabs], "owned_total": int(tot[0].item()),
-                       "owned_max_per_rank": int(mx[0].item()),
-                       "l2": "per-rank working set (> 126 MB of packed state + neighbour lists) exceeds L2; no flush"},
+            "config": _bench.workload_config(name, sc, n_total, n_total),
+            "sharding": {"slabs": slabs, "owned_total": int(tot[0].item()), "owned_max_per_rank": int(mx[0].item()),
+                         "ghost_layers": GHOST_LAYERS, "halo_capacity_records": sim.halo_cap,
+                         "exchange": "one NCCL send/recv group per step issued by libsph_b200.so inside the step's CUDA "
+                                     "graph, overlapped with the interior force pass; no host synchronisation in a step; "
+                                     "cuts re-balanced on the device every 8 steps"},
+            "parity_check": parity,
+            "strong_scaling": strong,
             "halo": {"bytes_per_step_all_ranks": halo_per_step,
                      "fraction_of_owned_state": halo_per_step / (64.0 * max(tot[0].item(), 1.0))},
             "clocks": clocks,
@@ -528,15 +507,10 @@ def bench_main(args):
                     "steps_per_s": Ke / float(e2e_s.item()), "steps": Ke,
                     "h2d_bytes_per_step": int(moved_t.item() / (2 * Ke)), "d2h_bytes_per_step": int(moved_t.item() / (2 * Ke)),
                     "note": "per rank and step: pinned-host -> device copy of the live records' position and velocity "
-                            "words, sharded step (NCCL halo exchange inside), device -> pinned-host copy back; max over ranks"},
+                            "words, sharded step (halo exchange inside), device -> pinned-host copy back; max over ranks"},
             "gpu_launches": int(tot[2].item()),
-            "roofline": {"kernel": "force pass (k_force_packed), slowest rank", "bound": "hbm",
-                         "achieved": _bench.FORCE_BYTES_PER_PARTICLE * float(roof_max[2].item()) / (float(roof_max[0].item()) * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s",
-                         "frac": _bench.FORCE_BYTES_PER_PARTICLE * float(roof_max[2].item()) / (float(roof_max[0].item()) * 1e-3) / 1e9 / peak,
-                         "traffic": None, "peak_source": peak_src, "avg_launch_ms": float(roof_max[0].item()),
-                         "density_launch_ms": float(roof_max[1].item()), "owned_particles_slowest_rank": int(roof_max[2].item()),
-                         "note": "per GPU; algorithmic 52 B x owned particles / CUDA-event time; pair kernels are issue bound"},
+            "roofline": roofline,
+            "stage_ms_slowest_rank": {"sort": float(roof_max[4].item()), "density": d_ms, "force_and_exchange": f_ms},
             "cpu_baseline": None,
             "notes": "cpu_baseline is reported by the N = 1 run and by --impl reference (bench.py contract)",
         }

@@ -124,11 +124,12 @@ private:
 
 inline void run_grid(dim3 grid, dim3 block, const std::function<void()> &body) {
     const int threads = (int)block.x;
-    for (unsigned b = 0; b < grid.x; ++b) {
+    for (unsigned bb = 0; bb < grid.x * grid.y; ++bb) {
+        const unsigned b = bb % grid.x, by = bb / grid.x;
         Block blk(threads);
         std::function<void(int)> fn = [&](int t) {
             threadIdx = uint3{(unsigned)t, 0, 0};
-            blockIdx = uint3{b, 0, 0};
+            blockIdx = uint3{b, by, 0};
             blockDim = block;
             gridDim = grid;
             tb = &blk;
@@ -277,7 +278,6 @@ inline float rsqrt_ftz(float x) { return 1.0f / std::sqrt(x); }
 inline float rcp_ftz(float x) { return 1.0f / x; }
 inline void ldg256(const float4 *p, float4 &a, float4 &b) { a = p[0]; b = p[1]; }
 inline int ldg_stream(const int32_t *p) { return *p; }
-inline void prefetch_l1(const void *) {}
 // mbarrier (arrival count 1): low word = completed phases, bits 32..62 = transaction count (signed: complete_tx may
 // run ahead of expect_tx), bit 63 = the arrive of the current phase has happened.  A phase completes when it has
 // arrived and its transaction count is zero.  Only the issuing lane writes; the waiting lanes poll.
@@ -326,7 +326,7 @@ typedef emu::Graph *cudaGraphExec_t;
 struct EmuEvent { std::chrono::steady_clock::time_point t; };
 typedef EmuEvent *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
-enum cudaStreamCaptureMode { cudaStreamCaptureModeThreadLocal };
+enum cudaStreamCaptureMode { cudaStreamCaptureModeThreadLocal, cudaStreamCaptureModeRelaxed };
 constexpr unsigned cudaStreamNonBlocking = 1;
 
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
@@ -344,6 +344,8 @@ inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyK
     return cudaSuccess;
 }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaMalloc(void **p, size_t n) { *p = std::malloc(n); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new emu::Stream(); return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete static_cast<emu::Stream *>(s); return cudaSuccess; }
 inline cudaError_t cudaStreamBeginCapture(cudaStream_t s, cudaStreamCaptureMode) {

@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--counts", type=int, nargs=3, default=[64, 24, 24])
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--vx", type=float, default=1.5)
+    ap.add_argument("--skew", type=int, default=0, help="shift every interior slab cut by this many layers at the start")
+    ap.add_argument("--rebalance-every", type=int, default=8)
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -44,35 +46,43 @@ def main():
     c = a.counts
     sc = scene.dam_break_box(c, domain_end=[2.5 * c[0] * d + 0.2, c[1] * d + 0.4, c[2] * d + 0.12], start=[0.06] * 3)
     sc["FluidBlocks"][0]["velocity"] = [a.vx, 0.0, 0.0]
-    sim, n_total = slab.build_sharded(sc, rank, world, dev)
-    owned_first = sim.owned_count()
-    for _ in range(a.steps):
-        sim.step()
-    x, v, x0 = sim.owned_state()
-    owned_last = sim.owned_count()
-    blob = {"x": x, "v": v, "x0": x0, "owned": (owned_first, owned_last), "halo": sim.halo_bytes}
+    transport = slab.GlooTransport() if (EMU and world > 1) else None
+    slabs = None
+    if a.skew:  # deliberately unbalanced start: every interior cut shifted, the balancer has to move them back
+        from sph_taichi_b200.scene import assemble_particles
+        cfg = SimConfig(sc)
+        arrays, _, _, _ = assemble_particles(cfg, 3, d)
+        gx = int(np.ceil(np.array(cfg.get_cfg("domainEnd")) / (2 * d)).astype(int)[0])
+        hist = np.bincount(slab.layer_of(arrays["x"], 2 * d), minlength=gx)[:gx]
+        base = slab.plan_slabs(hist, world)
+        cuts = [s_[0] for s_ in base] + [base[-1][1]]
+        cuts = [cuts[0]] + [c_ + a.skew for c_ in cuts[1:-1]] + [cuts[-1]]
+        slabs = [(cuts[r], cuts[r + 1]) for r in range(world)]
+    sim, n_total = slab.build_sharded(sc, rank, world, dev, rebalance_every=a.rebalance_every, slabs=slabs,
+                                      transport=transport)
+    first = sim.info()
+    sim.step(a.steps)
+    last = sim.info()
+    gathered = slab.gather_owned(sim)
+    meta = {"owned": (first["owned"], last["owned"]), "halo": 64 * last["halo_records_sent"],
+            "slab0": (first["x_lo"], first["x_hi"]), "slab1": (last["x_lo"], last["x_hi"])}
+    metas = [None] * world
     if world > 1:
-        gathered = [None] * world if rank == 0 else None
-        dist.gather_object(blob, gathered, dst=0)
+        dist.all_gather_object(metas, meta)
     else:
-        gathered = [blob]
+        metas = [meta]
     ok = True
     if rank == 0:
-        X = np.concatenate([g["x"] for g in gathered]); V = np.concatenate([g["v"] for g in gathered])
-        X0 = np.concatenate([g["x0"] for g in gathered])
         ps = ParticleSystem(SimConfig(sc), device=dev)
         s = ps.build_solver(); s.initialize(); s.step(a.steps)
-        rx, rv, rx0 = ps.x.to_numpy(), ps.v.to_numpy(), ps.x_0.to_numpy()
-        ks = np.lexsort((X0[:, 2], X0[:, 1], X0[:, 0])); kr = np.lexsort((rx0[:, 2], rx0[:, 1], rx0[:, 0]))
-        same_set = X0.shape == rx0.shape and np.array_equal(X0[ks], rx0[kr])
-        dx = float(np.abs(X[ks] - rx[kr]).max() / d) if same_set else float("inf")
-        dv = float(np.abs(V[ks] - rv[kr]).max()) if same_set else float("inf")
-        migrated = any(g["owned"][0] != g["owned"][1] for g in gathered)
-        ok = same_set and dx < 1e-3 and dv < 1e-2
-        print(json.dumps({"world": world, "particles": int(n_total), "steps": a.steps, "same_particle_set": bool(same_set),
-                          "max_dx_over_d": dx, "max_dv": dv, "migrated": bool(migrated),
-                          "owned_first_last": [list(map(int, g["owned"])) for g in gathered],
-                          "halo_bytes": [int(g["halo"]) for g in gathered], "ok": bool(ok)}))
+        cmp_ = slab.compare_with_single(gathered, ps, d)
+        migrated = any(m["owned"][0] != m["owned"][1] for m in metas)
+        moved = any(tuple(m["slab0"]) != tuple(m["slab1"]) for m in metas)
+        ok = cmp_["same_particle_set"] and cmp_["max_dx_over_d"] < 1e-3 and cmp_["max_dv"] < 1e-2
+        print(json.dumps(dict(cmp_, world=world, particles=int(n_total), steps=a.steps, migrated=bool(migrated),
+                              cuts_moved=bool(moved), owned_first_last=[list(map(int, m["owned"])) for m in metas],
+                              slabs_first=[list(m["slab0"]) for m in metas], slabs_last=[list(m["slab1"]) for m in metas],
+                              halo_bytes=[int(m["halo"]) for m in metas], ok=bool(ok))))
     if world > 1:
         flag = torch.tensor([1 if ok else 0], device=dev)
         dist.broadcast(flag, src=0)
