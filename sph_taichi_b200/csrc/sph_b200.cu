@@ -898,7 +898,13 @@ int sph_shard_step(SphCtx *ctx, int32_t nsteps, void *stream) {
     if (nsteps < 0) return SPH_E_ARG;
     if (!ctx->shard_begun) return fail(ctx, SPH_E_ARG, "sph_shard_begin was not called");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static const bool eager = std::getenv("SPH_SHARD_NO_GRAPH") != nullptr;  // debugging aid: launch every step un-graphed
     for (int s = 0; s < nsteps; ++s) {
+        if (eager) {
+            int rc = shard_sequence(ctx, st, /*compute=*/true, &ctx->launches);
+            if (rc) return rc;
+            continue;
+        }
         const int par = ctx->parity;
         if (!ctx->graph_shard[par]) {
             int rc = capture_shard_step(ctx, &ctx->graph_shard[par], &ctx->graph_shard_kernels[par]);
