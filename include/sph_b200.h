@@ -207,9 +207,10 @@ int sph_halo_exchange(SphCtx *ctx, void *stream);
  * own_end, sendL_begin, sendL_end, sendR_begin, sendR_end, recv_left, recv_right, n_sorted, status,
  * 0}; out_sent (may be NULL) = halo records sent so far */
 int sph_shard_info(SphCtx *ctx, int32_t *out16, uint64_t *out_sent, void *stream);
-/* ONE un-graphed sharded step with CUDA events between its stages; ms_out4 = {sort + bookkeeping, density,
- * boundary forces + pack, max(interior forces, halo exchange)}; synchronises */
-int sph_shard_profile_step(SphCtx *ctx, float *ms_out4, void *stream);
+/* ONE un-graphed sharded step with CUDA events between its stages; ms_out5 = {sort + bookkeeping, density,
+ * boundary forces + pack, max(interior forces, halo exchange), the exchange alone on the communication stream};
+ * synchronises */
+int sph_shard_profile_step(SphCtx *ctx, float *ms_out5, void *stream);
 int sph_state_offsets(SphCtx *ctx, uint64_t *out5); /* byte offsets of posm, veld, x0id, misc, acc in the workspace */
 
 /* ---- diagnostics ----------------------------------------------------------------------------- */

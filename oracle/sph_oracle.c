@@ -455,6 +455,44 @@ static void polar_rotation(const double A[9], double R[9]) {
         if (diff < 1e-30) break;
     }
     memcpy(R, X, sizeof(X));
+    /* The iteration yields the orthogonal polar factor Q with det Q = sign(det A).  ti.polar_decompose builds R from
+     * an SVD with proper rotations U, V (the sign goes to the smallest singular value): for det A < 0 that is
+     * R = Q (I - 2 v v^T), v = eigenvector of S = Q^T A with the smallest eigenvalue (cyclic Jacobi below). */
+    double detA = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+    if (detA < 0.0) {
+        double S[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) S[3 * r + c] = X[r] * A[c] + X[3 + r] * A[3 + c] + X[6 + r] * A[6 + c];
+        for (int r = 0; r < 3; ++r)
+            for (int c = r + 1; c < 3; ++c) S[3 * r + c] = S[3 * c + r] = 0.5 * (S[3 * r + c] + S[3 * c + r]);
+        for (int sweep = 0; sweep < 12; ++sweep)
+            for (int p = 0; p < 2; ++p)
+                for (int q = p + 1; q < 3; ++q) {
+                    double apq = S[3 * p + q];
+                    if (fabs(apq) < 1e-300) continue;
+                    double th = 0.5 * (S[3 * q + q] - S[3 * p + p]) / apq;
+                    double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                    double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+                    for (int k = 0; k < 3; ++k) {
+                        double skp = S[3 * k + p], skq = S[3 * k + q];
+                        S[3 * k + p] = cs * skp - sn * skq; S[3 * k + q] = sn * skp + cs * skq;
+                    }
+                    for (int k = 0; k < 3; ++k) {
+                        double spk = S[3 * p + k], sqk = S[3 * q + k];
+                        S[3 * p + k] = cs * spk - sn * sqk; S[3 * q + k] = sn * spk + cs * sqk;
+                        double vkp = V[3 * k + p], vkq = V[3 * k + q];
+                        V[3 * k + p] = cs * vkp - sn * vkq; V[3 * k + q] = sn * vkp + cs * vkq;
+                    }
+                }
+        int m = 0;
+        if (S[4] < S[3 * m + m]) m = 1;
+        if (S[8] < S[3 * m + m]) m = 2;
+        double v[3] = {V[m], V[3 + m], V[6 + m]};
+        for (int r = 0; r < 3; ++r) {
+            double qv = X[3 * r] * v[0] + X[3 * r + 1] * v[1] + X[3 * r + 2] * v[2];
+            for (int c = 0; c < 3; ++c) R[3 * r + c] = X[3 * r + c] - 2.0 * qv * v[c];
+        }
+    }
 }
 
 /* ---- sph_base.py:200-222: returns R (row-major) ------------------------------------- */

@@ -727,7 +727,7 @@ int shard_exchange(SphCtx *c, cudaStream_t st) {
 }
 
 // plan -> classify + sort -> info -> [density -> boundary forces] -> pack -> { exchange || interior forces }
-// ev[5] (optional): CUDA events recorded at the stage boundaries (sph_shard_profile_step)
+// ev[7] (optional): CUDA events at the stage boundaries, [5..6] around the exchange (sph_shard_profile_step)
 int shard_sequence(SphCtx *c, cudaStream_t st, bool compute, int64_t *kernels, cudaEvent_t *ev = nullptr) {
     if (ev) cudaEventRecord(ev[0], st);
     k_shard_plan<<<1, 32, 0, st>>>(c->P, c->S);
@@ -756,8 +756,10 @@ int shard_sequence(SphCtx *c, cudaStream_t st, bool compute, int64_t *kernels, c
     CUDA_TRY(c, cudaEventRecord(c->ev_packed, st));
     CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev_packed, 0));
 #endif
+    if (ev) cudaEventRecord(ev[5], cs);
     rc = shard_exchange(c, cs);
     if (rc) return rc;
+    if (ev) cudaEventRecord(ev[6], cs);
     if (compute) launch_pair_force_and_advect(c, st, nullptr, kernels, /*split_mode=*/2);
 #ifndef SPH_EMU
     CUDA_TRY(c, cudaEventRecord(c->ev_exchanged, cs));
@@ -933,18 +935,20 @@ int sph_shard_info(SphCtx *ctx, int32_t *out16, uint64_t *out_sent, void *stream
     return SPH_OK;
 }
 
-int sph_shard_profile_step(SphCtx *ctx, float *ms_out4, void *stream) {
+int sph_shard_profile_step(SphCtx *ctx, float *ms_out5, void *stream) {
     REQUIRE_SHARD(ctx);
-    if (!ms_out4) return SPH_E_ARG;
+    if (!ms_out5) return SPH_E_ARG;
     if (!ctx->shard_begun) return fail(ctx, SPH_E_ARG, "sph_shard_begin was not called");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaEvent_t ev[5];
-    for (int k = 0; k < 5; ++k) CUDA_TRY(ctx, cudaEventCreate(&ev[k]));
+    cudaEvent_t ev[7];
+    for (int k = 0; k < 7; ++k) CUDA_TRY(ctx, cudaEventCreate(&ev[k]));
     int rc = shard_sequence(ctx, st, /*compute=*/true, &ctx->launches, ev);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms_out4[k], ev[k], ev[k + 1]);
-    for (int k = 0; k < 5; ++k) cudaEventDestroy(ev[k]);
+    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms_out5[k], ev[k], ev[k + 1]);
+    ms_out5[4] = 0.f;
+    if (ctx->world > 1) cudaEventElapsedTime(&ms_out5[4], ev[5], ev[6]);
+    for (int k = 0; k < 7; ++k) cudaEventDestroy(ev[k]);
     return SPH_OK;
 }
 

@@ -622,6 +622,46 @@ __device__ void polar_rotation_f64(const double A[9], double R[9], bool &ok) {
         if (diff < 1e-30) break;
     }
     for (int i = 0; i < 9; ++i) R[i] = X[i];
+    // The iteration converges to the ORTHOGONAL polar factor Q, det Q = sign(det A).  ti.polar_decompose takes R
+    // from an SVD whose U and V are proper rotations (the smallest singular value carries the sign), i.e.
+    // R = Q (I - 2 v v^T) with v the eigenvector of S = Q^T A of smallest eigenvalue when det A < 0 (a collapsed
+    // or inverted body).  Cyclic Jacobi on the symmetric 3x3 S; only that rare case pays for it.
+    const double detA = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+    if (ok && detA < 0.0) {
+        double S[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) S[3 * r + c] = X[r] * A[c] + X[3 + r] * A[3 + c] + X[6 + r] * A[6 + c];  // Q^T A
+        for (int r = 0; r < 3; ++r)
+            for (int c = r + 1; c < 3; ++c) S[3 * r + c] = S[3 * c + r] = 0.5 * (S[3 * r + c] + S[3 * c + r]);
+        for (int sweep = 0; sweep < 12; ++sweep) {
+            for (int p = 0; p < 2; ++p)
+                for (int q = p + 1; q < 3; ++q) {
+                    const double apq = S[3 * p + q];
+                    if (fabs(apq) < 1e-300) continue;
+                    const double th = 0.5 * (S[3 * q + q] - S[3 * p + p]) / apq;
+                    const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+                    const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+                    for (int k = 0; k < 3; ++k) {  // S <- S J
+                        const double skp = S[3 * k + p], skq = S[3 * k + q];
+                        S[3 * k + p] = cs * skp - sn * skq; S[3 * k + q] = sn * skp + cs * skq;
+                    }
+                    for (int k = 0; k < 3; ++k) {  // S <- J^T S,  V <- V J
+                        const double spk = S[3 * p + k], sqk = S[3 * q + k];
+                        S[3 * p + k] = cs * spk - sn * sqk; S[3 * q + k] = sn * spk + cs * sqk;
+                        const double vkp = V[3 * k + p], vkq = V[3 * k + q];
+                        V[3 * k + p] = cs * vkp - sn * vkq; V[3 * k + q] = sn * vkp + cs * vkq;
+                    }
+                }
+        }
+        int m = 0;
+        if (S[4] < S[3 * m + m]) m = 1;
+        if (S[8] < S[3 * m + m]) m = 2;
+        const double v[3] = {V[m], V[3 + m], V[6 + m]};
+        for (int r = 0; r < 3; ++r) {
+            const double qv = X[3 * r] * v[0] + X[3 * r + 1] * v[1] + X[3 * r + 2] * v[2];
+            for (int c = 0; c < 3; ++c) R[3 * r + c] = X[3 * r + c] - 2.0 * qv * v[c];
+        }
+    }
 }
 
 // mode 0: compute_com -> out[3];  mode 1: store rest cm;  mode 2: solve_constraints.

@@ -72,7 +72,12 @@ class ParticleSystem:
             self.cfg, self.dim, self.particle_diameter)
         self.fluid_particle_num = counts["fluid"]
         self.solid_particle_num = counts["solid"]
-        self.particle_max_num = counts["total"]
+        # Emitter / dynamic particle count: the reference plans one (TODO at particle_system.py:85-86, FIXME at :324)
+        # but sizes every field for the scene's blocks only.  `emitterReserve` (Configuration key, default 0)
+        # reserves room for particles added with add_particles / add_cube AFTER initialize(); the neighbour
+        # search always works on particle_num[None] <= particle_max_num particles.
+        self.emitter_reserve = int(self.cfg.get_cfg("emitterReserve") or 0)
+        self.particle_max_num = counts["total"] + self.emitter_reserve
         self.num_rigid_bodies = len(self.cfg.get_rigid_blocks()) + len(self.cfg.get_rigid_bodies())
         self._n_fluid_blocks = len(self.cfg.get_fluid_blocks())
         self.particle_num = ScalarField(0)
@@ -115,7 +120,7 @@ class ParticleSystem:
         # ---- engine ----
         self._dt = self.cfg.get_cfg("timeStepSize") or 1e-4
         # capacity: every solid object could be registered for shape matching
-        self._engine = _engine.Engine(self._make_params(), n_max=n, n_solid=self.solid_particle_num,
+        self._engine = _engine.Engine(self._make_params(), n_max=n, n_solid=self.solid_particle_num + self.emitter_reserve,
                                       n_bodies=self.num_rigid_bodies, device=dev)
         self._fields_dirty = True   # public tensors hold data the engine has not packed yet
         self._engine_ahead = False  # engine state is newer than the public tensors
@@ -131,6 +136,7 @@ class ParticleSystem:
                                arrays["pressure"][sl], arrays["material"][sl], arrays["is_dynamic"][sl],
                                arrays["color"][sl])
             start += cnt
+        self._filled = True
 
     # ------------------------------------------------------------------------------------
     def _solver_constants(self):
@@ -242,7 +248,8 @@ class ParticleSystem:
         p0 = int(self.particle_num[None])
         k = int(new_particles_num)
         if p0 + k > self.particle_max_num:
-            raise ValueError("add_particles: exceeds particle_max_num (the reference has no emitter either)")
+            raise ValueError(f"add_particles: {p0} + {k} particles exceed particle_max_num = {self.particle_max_num} "
+                             "(reserve room with the Configuration key emitterReserve)")
         col = np.asarray(new_particles_color)
         if col.size and (col.min() < 0 or col.max() > 255):
             raise ValueError("colour components must be in 0..255")
@@ -267,6 +274,10 @@ class ParticleSystem:
         t["is_dynamic"][sl] = up(new_particles_is_dynamic, np.int32).reshape(k)
         t["color"][sl] = up(col, np.int32).reshape(k, 3)
         self.particle_num[None] = p0 + k
+        if getattr(self, "_filled", False):  # emitter: particles added after construction
+            mat = np.asarray(new_particles_material).reshape(-1)
+            self.fluid_particle_num += int((mat == self.material_fluid).sum())
+            self.solid_particle_num += int((mat == self.material_solid).sum())
         self._touch()
 
     def initialize_particle_system(self):

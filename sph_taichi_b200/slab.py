@@ -185,10 +185,11 @@ class ShardedSimulation:
     def profile_step(self):
         """ONE un-graphed step with CUDA events between the stages (synchronises)."""
         e = self.eng
-        buf = (C.c_float * 4)()
+        buf = (C.c_float * 5)()
         e._check(e.lib.sph_shard_profile_step(e.ctx, buf, e._stream()), "sph_shard_profile_step")
         self.steps_done += 1
-        return {"sort_ms": buf[0], "density_ms": buf[1], "boundary_force_pack_ms": buf[2], "interior_force_or_exchange_ms": buf[3]}
+        return {"sort_ms": buf[0], "density_ms": buf[1], "boundary_force_pack_ms": buf[2],
+                "interior_force_or_exchange_ms": buf[3], "exchange_ms": buf[4]}
 
     def info(self):
         """The device-resident step state (synchronising read); raises on a capacity / out-of-grid flag."""

@@ -207,6 +207,34 @@ def test_rigid_solve_recovers_rotation_gpu():
     assert np.allclose(x1[sel1], (x01[sel1] - cm0) @ Ry.T + cm0 + shift, atol=2e-5)
 
 
+def test_rigid_solve_of_an_inverted_body_is_a_proper_rotation():
+    """A mirrored (inverted) body: det A < 0.  ti.polar_decompose returns a PROPER rotation (its SVD keeps U and V
+    rotations, the sign goes to the smallest singular value); the orthogonal polar factor would be a reflection."""
+    o, ps, solver = _pair(mixed_scene(with_static=False), register_blocks=(2,))
+    solver.initialize(); o.initialize()
+    oid = 2
+    x = ps.x.to_numpy(); x0 = ps.x_0.to_numpy(); sel = ps.object_id.to_numpy() == oid
+    cm0 = ps.rigid_rest_cm[oid].astype(np.float64)
+    th = 0.3
+    Rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    M = Rz @ np.diag([1.0, 0.8, -0.6])  # mirrored and squashed along z: det < 0, distinct singular values
+    x[sel] = ((x0[sel] - cm0) @ M.T + cm0).astype(np.float32)
+    ps.x.from_numpy(x)
+    osel = o.object_id == oid
+    o.x[osel] = ((o.x_0[osel] - cm0) @ M.T + cm0).astype(np.float32)
+    ps.initialize_particle_system(); o.initialize_particle_system()
+    R = solver.solve_constraints(oid).cpu().numpy().astype(np.float64)
+    Ro = o.solve_constraints(oid).astype(np.float64)
+    q = (x0[sel] - cm0).astype(np.float64)
+    A = M @ (q.T @ q)  # sph_base.py:204-211 with equal masses: A = sum (x - c)(x_0 - c_0)^T = M sum q q^T
+    U, s_, Vt = np.linalg.svd(A)
+    want = U @ np.diag([1, 1, np.linalg.det(U @ Vt)]) @ Vt  # the sign goes to the SMALLEST singular value of A
+    assert abs(np.linalg.det(R) - 1.0) < 1e-4 and np.allclose(R @ R.T, np.eye(3), atol=1e-4)
+    assert np.allclose(R, want, atol=2e-3) and np.allclose(Ro, want, atol=2e-3)
+    assert np.allclose(R, Ro, atol=1e-4)
+    assert ps._engine.read_status() & 2 == 0
+
+
 def test_dump_and_invariants_dragon_bath_full_size():
     """BASELINE cfg 2 at full size: size-independent properties after real steps."""
     from sph_taichi_b200 import ParticleSystem, SimConfig, scene
@@ -452,3 +480,54 @@ def test_random_scatter_state_vs_oracle(seed, fill):
     # close random pairs give accelerations of 1e5 m/s^2: the position error is dt times the velocity error
     dt = sc["Configuration"]["timeStepSize"]
     assert np.abs(ps.x.to_numpy() - o.x).max() <= dt * 10 * REL * float(np.abs(o.v).max()) + 1e-6
+
+
+def test_emitter_adds_a_block_mid_run():
+    """SURVEY section 8f rank 4 (the reference's planned emitter, particle_system.py:85-86): with
+    `emitterReserve` a block is added through add_cube AFTER 12 steps; the run continues and matches an oracle
+    that is handed the same 12-step state plus the same new block."""
+    from oracle.sph_oracle import OracleSim
+    from sph_taichi_b200 import ParticleSystem, SimConfig, scene
+    d = 0.02
+    base = scene.dam_break_box([10, 10, 10], domain_end=[0.8, 0.8, 0.6], start=[0.1, 0.06, 0.1])
+    lower, size = np.array([0.42, 0.06, 0.1]), np.array([8 * d - 0.5 * d, 6 * d - 0.5 * d, 8 * d - 0.5 * d])
+    sc = {k: (dict(v) if isinstance(v, dict) else list(v)) for k, v in base.items()}
+    sc["Configuration"]["emitterReserve"] = 8 * 6 * 8
+    ps = ParticleSystem(SimConfig(sc))
+    assert ps.particle_max_num == 1000 + 384 and ps.particle_num[None] == 1000
+    solver = ps.build_solver()
+    solver.initialize()
+    solver.step(12)
+    ps.add_cube(object_id=0, lower_corner=lower, cube_size=size, material=1, is_dynamic=1, color=(50, 100, 200),
+                density=1000.0, velocity=[0.0, -1.0, 0.0])
+    assert ps.particle_num[None] == 1384 and ps.fluid_particle_num == 1384
+    with pytest.raises(ValueError, match="emitterReserve"):
+        ps.add_cube(object_id=0, lower_corner=lower, cube_size=size, material=1, is_dynamic=1)
+    solver.step(12)
+    assert ps._engine.check_status() == 0
+
+    # oracle: the 1000-particle scene for 12 steps, then the same state + the new block in a 1384-particle oracle
+    o1 = OracleSim(base)
+    o1.initialize()
+    for _ in range(12):
+        o1.step()
+    both = {k: (dict(v) if isinstance(v, dict) else list(v)) for k, v in base.items()}
+    blk = dict(base["FluidBlocks"][0])
+    blk.update(start=[float(v) for v in lower], end=[float(v) for v in lower + size], velocity=[0.0, -1.0, 0.0])
+    both["FluidBlocks"] = [base["FluidBlocks"][0], blk]
+    o2 = OracleSim(both)
+    assert o2.n == 1384
+    k1 = order_by_x0(o1.x_0)
+    old = np.arange(1000)  # the first block's particles come first in the assembly order
+    k2 = old[order_by_x0(o2.x_0[:1000])]
+    assert np.array_equal(o2.x_0[k2], o1.x_0[k1])
+    o2.x[k2] = o1.x[k1]; o2.v[k2] = o1.v[k1]
+    for _ in range(12):
+        o2.step()
+    n = 1384
+    x, x0 = ps.x.to_numpy()[:n], ps.x_0.to_numpy()[:n]
+    kg, ko = order_by_x0(x0), order_by_x0(o2.x_0)
+    assert np.array_equal(x0[kg], o2.x_0[ko])
+    assert np.abs(x[kg] - o2.x[ko]).max() / d < 1e-4
+    assert _maxrel(ps.v.to_numpy()[:n][kg], o2.v[ko]) < 1e-4
+    assert _maxrel(ps.density.to_numpy()[:n][kg], o2.density[ko]) < 10 * REL

@@ -1,22 +1,15 @@
 #!/bin/bash
-# Round-2 GPU call 5 (2 GPUs): the sharded engine on real NCCL.
+# Round-2 GPU call 6 (2 GPUs): where the sharded step spends its time; NCCL channel settings.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-export NCCL_DEBUG=WARN
+run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port $1 tools/shard_timing.py "${@:2}" 2>&1 | grep "^{"; }
 {
-echo "== nvidia-smi"; nvidia-smi --query-gpu=index,name --format=csv,noheader
-echo "== slab parity, 2 ranks, eager (no graph)"
-SPH_SHARD_NO_GRAPH=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29533 tools/check_slab_parity.py --counts 64 24 24 --steps 60 2>&1 | grep -v "^\*\|OMP_NUM" | tail -6
-echo "== slab parity, 2 ranks, graph"
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29534 tools/check_slab_parity.py --counts 128 48 48 --steps 120 --rebalance-every 4 2>&1 | grep -v "^\*\|OMP_NUM" | tail -6
-echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-echo "== bench --gpus 2"
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29535 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_r02_n2.json 2> gpurun_out/bench_r02_n2.err; tail -c 1500 gpurun_out/bench_r02_n2.err; python - <<'P'
-import json
-try:
-    d=json.loads(open('gpurun_out/bench_r02_n2.json').read().strip().splitlines()[-1])
-    for k in ('value','ms_per_step','parity_check','strong_scaling','halo','stage_ms_slowest_rank','e2e','sharding'): print(k, json.dumps(d.get(k))[:400])
-except Exception as e: print("bench parse failed", e, open('gpurun_out/bench_r02_n2.json').read()[-800:])
-P
-} > gpurun_out/call05.log 2>&1
-tail -50 gpurun_out/call05.log
+echo "== default"; run 29541 --tag default
+echo "== capacity 1.1"; run 29542 --tag cap1.1 --capacity 1.1
+echo "== p2p nchannels 16..32"; NCCL_MIN_P2P_NCHANNELS=16 NCCL_MAX_P2P_NCHANNELS=32 run 29543 --tag ch16-32
+echo "== p2p nchannels 32"; NCCL_MIN_P2P_NCHANNELS=32 NCCL_MAX_P2P_NCHANNELS=32 run 29544 --tag ch32
+echo "== p2p nchannels 4"; NCCL_MIN_P2P_NCHANNELS=4 NCCL_MAX_P2P_NCHANNELS=4 run 29545 --tag ch4
+echo "== NCCL_P2P_LEVEL NVL + chunk"; NCCL_P2P_NET_CHUNKSIZE=524288 NCCL_BUFFSIZE=16777216 run 29546 --tag buff16m
+echo "== pytest new tests"; timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "emitter or inverted or slab" 2>&1 | tail -3
+} > gpurun_out/call06.log 2>&1
+tail -30 gpurun_out/call06.log
