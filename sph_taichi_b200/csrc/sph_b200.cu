@@ -144,8 +144,10 @@ struct SphCtx {
     bool shard_begun = false;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_packed = nullptr, ev_exchanged = nullptr;
-    cudaGraphExec_t graph_shard[2] = {nullptr, nullptr};
-    int64_t graph_shard_kernels[2] = {0, 0};
+    cudaGraphExec_t graph_shard[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [parity][wide exchange]
+    int64_t graph_shard_kernels[2][2] = {{0, 0}, {0, 0}};
+    int32_t narrow_cap = 0;      // records per side of the usual (sgw + 1 layers) exchange; halo_cap = sgw + 2 layers
+    int64_t shard_sequences = 0;  // sequences run so far (begin = 0): sequence q feeds the plan kernel of q + 1
 };
 
 namespace {
@@ -218,7 +220,8 @@ void drop_graphs(SphCtx *c) {
     for (int k = 0; k < 2; ++k) {
         if (c->graph[k]) { cudaGraphExecDestroy(c->graph[k]); c->graph[k] = nullptr; }
         if (c->graph_multi[k]) { cudaGraphExecDestroy(c->graph_multi[k]); c->graph_multi[k] = nullptr; }
-        if (c->graph_shard[k]) { cudaGraphExecDestroy(c->graph_shard[k]); c->graph_shard[k] = nullptr; }
+        for (int w = 0; w < 2; ++w)
+            if (c->graph_shard[k][w]) { cudaGraphExecDestroy(c->graph_shard[k][w]); c->graph_shard[k][w] = nullptr; }
     }
 }
 
@@ -699,12 +702,12 @@ int nccl_recv(void *user, void *buf, uint64_t bytes, int32_t peer, void *stream)
 // records of the CURRENT buffer set (left neighbour's at n - 2 * halo_cap, right neighbour's at n - halo_cap),
 // their headers in the device step state.  Fixed-size messages (the record count travels in the header), so the
 // whole group can be captured in a CUDA graph.
-int shard_exchange(SphCtx *c, cudaStream_t st) {
+int shard_exchange(SphCtx *c, cudaStream_t st, bool wide) {
     if (c->world <= 1) return SPH_OK;
     if (!c->has_transport) return fail(c, SPH_E_ARG, "no transport: call sph_comm_init_nccl or sph_comm_set_transport first");
     const SphTransport t = c->transport;
     const DevArrays S = c->S;
-    const uint64_t bytes = (uint64_t)c->P.halo_cap * 16;
+    const uint64_t bytes = (uint64_t)(wide ? c->P.halo_cap : c->narrow_cap) * 16;
     float4 *cur[4] = {S.posm, S.veld, S.x0id, S.misc};
     TRANSPORT_OP(st, t.group_start(t.user));
     for (int side = 0; side < 2; ++side) {
@@ -728,13 +731,14 @@ int shard_exchange(SphCtx *c, cudaStream_t st) {
 
 // plan -> classify + sort -> info -> [density -> boundary forces] -> pack -> { exchange || interior forces }
 // ev[7] (optional): CUDA events at the stage boundaries, [5..6] around the exchange (sph_shard_profile_step)
-int shard_sequence(SphCtx *c, cudaStream_t st, bool compute, int64_t *kernels, cudaEvent_t *ev = nullptr) {
+// wide: this sequence's exchange feeds a re-balancing step and carries sgw + 2 layers instead of sgw + 1
+int shard_sequence(SphCtx *c, cudaStream_t st, bool compute, bool wide, int64_t *kernels, cudaEvent_t *ev = nullptr) {
     if (ev) cudaEventRecord(ev[0], st);
     k_shard_plan<<<1, 32, 0, st>>>(c->P, c->S);
     *kernels += 1;
     int rc = launch_neighbor_build(c, st, nullptr, kernels, /*move_acc=*/false);
     if (rc) return rc;
-    k_shard_info<<<1, 32, 0, st>>>(c->P, c->S);
+    k_shard_info<<<1, 32, 0, st>>>(c->P, c->S, c->P.sgw + (wide ? 2 : 1), wide ? c->P.halo_cap : c->narrow_cap);
     *kernels += 1;
     if (ev) cudaEventRecord(ev[1], st);
     if (compute) {
@@ -757,7 +761,7 @@ int shard_sequence(SphCtx *c, cudaStream_t st, bool compute, int64_t *kernels, c
     CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev_packed, 0));
 #endif
     if (ev) cudaEventRecord(ev[5], cs);
-    rc = shard_exchange(c, cs);
+    rc = shard_exchange(c, cs, wide);
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[6], cs);
     if (compute) launch_pair_force_and_advect(c, st, nullptr, kernels, /*split_mode=*/2);
@@ -771,7 +775,7 @@ int shard_sequence(SphCtx *c, cudaStream_t st, bool compute, int64_t *kernels, c
     return SPH_OK;
 }
 
-int capture_shard_step(SphCtx *ctx, cudaGraphExec_t *out, int64_t *kernels_out) {
+int capture_shard_step(SphCtx *ctx, bool wide, cudaGraphExec_t *out, int64_t *kernels_out) {
     const int par = ctx->parity;
     cudaGraph_t g = nullptr;
     int64_t kernels = 0;
@@ -779,7 +783,7 @@ int capture_shard_step(SphCtx *ctx, cudaGraphExec_t *out, int64_t *kernels_out) 
     cudaStream_t cs = ctx->capture_stream;
     // relaxed: NCCL may issue CUDA calls of its own while its send / recv kernels are being captured
     CUDA_TRY(ctx, cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
-    int rc = shard_sequence(ctx, cs, /*compute=*/true, &kernels);
+    int rc = shard_sequence(ctx, cs, /*compute=*/true, wide, &kernels);
     cudaError_t e = cudaStreamEndCapture(cs, &g);
     ctx->parity = par;  // capture advanced the host-side parity exactly as a real step does; rewind
     bind_arrays(ctx);
@@ -863,6 +867,8 @@ int sph_shard_configure(SphCtx *ctx, int32_t x_lo, int32_t x_hi, int32_t ghost_l
     ctx->P.slab_on = 1; ctx->P.sgw = ghost_layers; ctx->P.halo_cap = (int32_t)halo_capacity;
     ctx->P.has_left = ctx->rank > 0; ctx->P.has_right = ctx->rank + 1 < ctx->world;
     ctx->P.rebalance_every = rebalance_every;
+    ctx->narrow_cap = (int32_t)((halo_capacity * (ghost_layers + 1) + ghost_layers + 1) / (ghost_layers + 2));
+    ctx->shard_sequences = 0;
     ctx->P.n = (int32_t)ctx->n_max;  // from here on n is the CAPACITY; the live count is device state
     ctx->shard_begun = false;
     bind_arrays(ctx);
@@ -878,21 +884,29 @@ int sph_shard_configure(SphCtx *ctx, int32_t x_lo, int32_t x_hi, int32_t ghost_l
     return SPH_OK;
 }
 
+// the exchange at the end of sequence q delivers the records plan kernel q + 1 works on; that one re-balances
+static inline bool shard_wide(const SphCtx *c) {
+    const int64_t next_plan = c->shard_sequences + 1;
+    return c->P.rebalance_every > 0 && next_plan % c->P.rebalance_every == 0;
+}
+
 #define REQUIRE_SHARD(ctx)                                                                              \
     if (!(ctx)) return SPH_E_ARG;                                                                       \
     if (!(ctx)->P.slab_on || !(ctx)->shard_buf) return fail((ctx), SPH_E_ARG, "sph_shard_configure was not called");
 
 int sph_shard_begin(SphCtx *ctx, void *stream) {
     REQUIRE_SHARD(ctx);
-    int rc = shard_sequence(ctx, static_cast<cudaStream_t>(stream), /*compute=*/false, &ctx->launches);
+    ctx->shard_sequences = 0;
+    int rc = shard_sequence(ctx, static_cast<cudaStream_t>(stream), /*compute=*/false, shard_wide(ctx), &ctx->launches);
     if (rc) return rc;
+    ctx->shard_sequences = 1;
     ctx->shard_begun = true;
     return SPH_OK;
 }
 
 int sph_halo_exchange(SphCtx *ctx, void *stream) {
     REQUIRE_SHARD(ctx);
-    return shard_exchange(ctx, static_cast<cudaStream_t>(stream));
+    return shard_exchange(ctx, static_cast<cudaStream_t>(stream), /*wide=*/true);
 }
 
 int sph_shard_step(SphCtx *ctx, int32_t nsteps, void *stream) {
@@ -902,20 +916,23 @@ int sph_shard_step(SphCtx *ctx, int32_t nsteps, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static const bool eager = std::getenv("SPH_SHARD_NO_GRAPH") != nullptr;  // debugging aid: launch every step un-graphed
     for (int s = 0; s < nsteps; ++s) {
+        const bool wide = shard_wide(ctx);
         if (eager) {
-            int rc = shard_sequence(ctx, st, /*compute=*/true, &ctx->launches);
+            int rc = shard_sequence(ctx, st, /*compute=*/true, wide, &ctx->launches);
             if (rc) return rc;
+            ctx->shard_sequences += 1;
             continue;
         }
         const int par = ctx->parity;
-        if (!ctx->graph_shard[par]) {
-            int rc = capture_shard_step(ctx, &ctx->graph_shard[par], &ctx->graph_shard_kernels[par]);
+        if (!ctx->graph_shard[par][wide]) {
+            int rc = capture_shard_step(ctx, wide, &ctx->graph_shard[par][wide], &ctx->graph_shard_kernels[par][wide]);
             if (rc) return rc;
         }
-        CUDA_TRY(ctx, cudaGraphLaunch(ctx->graph_shard[par], st));
-        ctx->launches += ctx->graph_shard_kernels[par];
+        CUDA_TRY(ctx, cudaGraphLaunch(ctx->graph_shard[par][wide], st));
+        ctx->launches += ctx->graph_shard_kernels[par][wide];
         ctx->parity = par ^ 1;
         bind_arrays(ctx);
+        ctx->shard_sequences += 1;
     }
     return SPH_OK;
 }
@@ -942,8 +959,9 @@ int sph_shard_profile_step(SphCtx *ctx, float *ms_out5, void *stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaEvent_t ev[7];
     for (int k = 0; k < 7; ++k) CUDA_TRY(ctx, cudaEventCreate(&ev[k]));
-    int rc = shard_sequence(ctx, st, /*compute=*/true, &ctx->launches, ev);
+    int rc = shard_sequence(ctx, st, /*compute=*/true, shard_wide(ctx), &ctx->launches, ev);
     if (rc) return rc;
+    ctx->shard_sequences += 1;
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms_out5[k], ev[k], ev[k + 1]);
     ms_out5[4] = 0.f;

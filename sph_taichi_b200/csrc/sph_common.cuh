@@ -104,9 +104,11 @@ enum {
     SD_OWN0, SD_OWN1,                            // index range of the owned cell layers
     SD_SEND_L0, SD_SEND_L1, SD_SEND_R0, SD_SEND_R1,  // index ranges packed for the left / right neighbour
     SD_RECV_L, SD_RECV_R,                        // records received for THIS step's classification
-    SD_N_SORTED, SD_FLAGS, SD_SPARE,
+    SD_N_SORTED, SD_FLAGS, SD_DENS0,                   // [DENS0, DENS1): index range that needs densities
+    // (DENS1 follows the headers)
     SD_HDR_L = 16, SD_HDR_R = 32,                // headers received from the left / right neighbour
     SD_SENT_LO = 48, SD_SENT_HI,                 // records sent so far (64-bit, for the halo statistics)
+    SD_DENS1 = 50,
     SD_INTS = 64
 };
 constexpr int SHARD_MIN_WIDTH = 5;  // a slab gives a layer away only while it is wider than this (ghost band 2 + send range 4 must fit)

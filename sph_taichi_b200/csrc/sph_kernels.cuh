@@ -104,18 +104,18 @@ __global__ void k_hash_count(DevParams P, DevArrays S) {
         }
         S.cid[i] = c;
     }
-    // the trash bucket collects ~10 % of all records in slab mode: one atomic per warp, not per lane
-    // The histogram atomic also hands out the arrival ticket inside the cell, which k_bucket turns
-    // into a slot after the scan -- no second round of atomics.
-    const unsigned trash = __ballot_sync(0xffffffffu, active && c == P.C);
-    if (active && c != P.C) S.ticket[i] = atomicAdd(S.cell_end + c, 1);
-    if (trash) {
-        const int lane = threadIdx.x & 31, leader = __ffs(trash) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(S.cell_end + P.C, __popc(trash));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (active && c == P.C) S.ticket[i] = base + __popc(trash & ((1u << lane) - 1u));
-    }
+    // The histogram atomic also hands out the arrival ticket inside the cell, which k_bucket turns into a slot
+    // after the scan -- no second round of atomics.  The input is the previous step's sorted order, so the lanes of
+    // a warp hold 4-5 distinct cells (and the trash bucket of a sharded step ~10 % of all records): ONE atomic per
+    // distinct cell and warp (MATCH.ANY), the lanes of a group take consecutive tickets.  Any ticket order is
+    // fine -- k_rank_move restores the stable order.
+    const int lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(0xffffffffu, c);  // inactive lanes (c == -1) form their own group
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (active && lane == leader) base = atomicAdd(S.cell_end + c, __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (active) S.ticket[i] = base + __popc(peers & ((1u << lane) - 1u));
 }
 
 // ---- x-slab sharding: the per-step bookkeeping that used to live on the host (round 1: an all-gather of the
@@ -148,9 +148,10 @@ __global__ void k_shard_plan(DevParams P, DevArrays S) {
     sd[SD_STEP] = step + 1;
 }
 
-// After the sort: live count, owned range and the index ranges of the boundary layers to send (sgw + 2 layers
-// per side: one more than the ghost band needs, so that a cut may move by a layer in any step), and the headers.
-__global__ void k_shard_info(DevParams P, DevArrays S) {
+// After the sort: live count, owned range and the index ranges of the boundary layers to send, and the headers.
+// send_layers = sgw + 1 (what the ghost band plus this step's migrants need) or, for the exchange that feeds a
+// re-balancing step, sgw + 2 (the cut may then move by a layer); the host picks the graph variant by step number.
+__global__ void k_shard_info(DevParams P, DevArrays S, int send_layers, int send_cap) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int32_t *sd = S.sd;
     const int layer = P.gy * P.gz;
@@ -162,18 +163,21 @@ __global__ void k_shard_info(DevParams P, DevArrays S) {
     };
     const int n_live = S.cell_end[P.C - 1], n_sorted = S.cell_end[P.C];
     const int o0 = start_of_layer(sx0), o1 = start_of_layer(sx1);
-    int l0 = o0, l1 = start_of_layer(min(sx0 + P.sgw + 2, sx1));
-    int r0 = start_of_layer(max(sx1 - P.sgw - 2, sx0)), r1 = o1;
+    int l0 = o0, l1 = start_of_layer(min(sx0 + send_layers, sx1));
+    int r0 = start_of_layer(max(sx1 - send_layers, sx0)), r1 = o1;
     if (!P.has_left) l1 = l0;
     if (!P.has_right) r0 = r1;
     uint32_t flags = 0u;
-    if (l1 - l0 > P.halo_cap) { l1 = l0 + P.halo_cap; flags |= SPH_STATUS_HALO_CAPACITY; }
-    if (r1 - r0 > P.halo_cap) { r0 = r1 - P.halo_cap; flags |= SPH_STATUS_HALO_CAPACITY; }
+    if (l1 - l0 > send_cap) { l1 = l0 + send_cap; flags |= SPH_STATUS_HALO_CAPACITY; }
+    if (r1 - r0 > send_cap) { r0 = r1 - send_cap; flags |= SPH_STATUS_HALO_CAPACITY; }
     if (n_sorted > P.n - 2 * P.halo_cap) flags |= SPH_STATUS_SHARD_CAPACITY;  // the sort ran into the receive regions
     if (flags) atomicOr(S.status, flags);
     sd[SD_N_LIVE] = n_live; sd[SD_N_SORTED] = n_sorted;
     sd[SD_OWNED] = o1 - o0; sd[SD_OWN0] = o0; sd[SD_OWN1] = o1;
     sd[SD_SEND_L0] = l0; sd[SD_SEND_L1] = l1; sd[SD_SEND_R0] = r0; sd[SD_SEND_R1] = r1;
+    // densities are needed for the owned particles and the FIRST ghost layer of each side (the second one only
+    // serves as neighbours of the first): one contiguous index range
+    sd[SD_DENS0] = start_of_layer(sx0 - 1); sd[SD_DENS1] = start_of_layer(sx1 + 1);
     sd[SD_FLAGS] = (int32_t)(*S.status);
     unsigned long long sent = ((unsigned long long)(uint32_t)sd[SD_SENT_HI] << 32) | (uint32_t)sd[SD_SENT_LO];
     sent += (unsigned long long)(l1 - l0) + (unsigned long long)(r1 - r0);
@@ -207,9 +211,15 @@ __global__ void k_shard_pack(DevParams P, DevArrays S) {
 // ~7 launches).  Here: ONE launch, decoupled look-back.  Each CTA takes a tile in arrival
 // order, scans it with warp shuffles + shared memory, publishes {status, value} as one 64-bit
 // word and resolves its exclusive prefix by looking back over predecessor tiles a warp at a time.
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_IPT = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_IPT;
+#ifndef SCAN_THREADS_VALUE
+#define SCAN_THREADS_VALUE 512
+#endif
+#ifndef SCAN_IPT_VALUE
+#define SCAN_IPT_VALUE 16
+#endif
+constexpr int SCAN_THREADS = SCAN_THREADS_VALUE;
+constexpr int SCAN_IPT = SCAN_IPT_VALUE;  // multiple of 4 (128-bit loads); 8192 cells per tile: 58 tiles for 469 K cells --
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_IPT;  // one wave, at most two look-back rounds (was 2048 / 229 tiles)
 #define SCAN_ST_AGG 1ull
 #define SCAN_ST_PREFIX 2ull
 
@@ -226,9 +236,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int32_t *__restrict__ dat
 
     int v[SCAN_IPT];
     if (base + SCAN_IPT <= C) {
-        int4 a = *reinterpret_cast<const int4 *>(data + base);
-        int4 b = *reinterpret_cast<const int4 *>(data + base + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+        for (int q = 0; q < SCAN_IPT / 4; ++q) {
+            int4 a = *reinterpret_cast<const int4 *>(data + base + 4 * q);
+            v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < SCAN_IPT; ++k) v[k] = (base + k < C) ? data[base + k] : 0;
@@ -285,10 +297,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int32_t *__restrict__ dat
     __syncthreads();
     const int off = s_excl + s_warp[warp] + (incl - tsum);
     if (base + SCAN_IPT <= C) {
-        int4 a = make_int4(v[0] + off, v[1] + off, v[2] + off, v[3] + off);
-        int4 b = make_int4(v[4] + off, v[5] + off, v[6] + off, v[7] + off);
-        *reinterpret_cast<int4 *>(data + base) = a;
-        *reinterpret_cast<int4 *>(data + base + 4) = b;
+#pragma unroll
+        for (int q = 0; q < SCAN_IPT / 4; ++q)
+            *reinterpret_cast<int4 *>(data + base + 4 * q) =
+                make_int4(v[4 * q] + off, v[4 * q + 1] + off, v[4 * q + 2] + off, v[4 * q + 3] + off);
     } else {
 #pragma unroll
         for (int k = 0; k < SCAN_IPT; ++k)
@@ -837,7 +849,9 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
     mbar_fence_init();
     __syncwarp();
 
-    bool live = i < (P.slab_on ? S.sd[SD_N_LIVE] : P.n);  // sharded: the trash bucket behind n_live is not touched
+    // sharded: owned particles + the first ghost layer per side (one index range; ghosts further out and the
+    // trash bucket are neighbours at most)
+    bool live = P.slab_on ? (i >= S.sd[SD_DENS0] && i < S.sd[SD_DENS1]) : i < P.n;
     float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), mi = pi;
     uint32_t fl = 0;
     if (live) { pi = S.posm[i]; mi = S.misc[i]; fl = __float_as_uint(mi.z); }

@@ -189,6 +189,14 @@ inline unsigned __ballot_sync(unsigned, int pred) {
         return r;
     });
 }
+inline unsigned __match_any_sync(unsigned, int v) {
+    const int me = emu::lane;
+    return emu::collective((uint32_t)v, [me](const uint32_t *s, uint32_t alive) {
+        uint32_t r = 0;
+        for (int l = 0; l < 32; ++l) if (((alive >> l) & 1u) && s[l] == s[me]) r |= 1u << l;
+        return r;
+    });
+}
 inline uint32_t emu_shfl_bits(uint32_t v, int src) {
     return emu::collective(v, [src](const uint32_t *s, uint32_t) { return s[src & 31]; });
 }

@@ -1,15 +1,19 @@
 #!/bin/bash
-# Round-2 GPU call 6 (2 GPUs): where the sharded step spends its time; NCCL channel settings.
+# Round-2 GPU call 7 (1 GPU): sort-chain changes (8192-cell scan tiles, warp-aggregated histogram), full test suite, bench line.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port $1 tools/shard_timing.py "${@:2}" 2>&1 | grep "^{"; }
 {
-echo "== default"; run 29541 --tag default
-echo "== capacity 1.1"; run 29542 --tag cap1.1 --capacity 1.1
-echo "== p2p nchannels 16..32"; NCCL_MIN_P2P_NCHANNELS=16 NCCL_MAX_P2P_NCHANNELS=32 run 29543 --tag ch16-32
-echo "== p2p nchannels 32"; NCCL_MIN_P2P_NCHANNELS=32 NCCL_MAX_P2P_NCHANNELS=32 run 29544 --tag ch32
-echo "== p2p nchannels 4"; NCCL_MIN_P2P_NCHANNELS=4 NCCL_MAX_P2P_NCHANNELS=4 run 29545 --tag ch4
-echo "== NCCL_P2P_LEVEL NVL + chunk"; NCCL_P2P_NET_CHUNKSIZE=524288 NCCL_BUFFSIZE=16777216 run 29546 --tag buff16m
-echo "== pytest new tests"; timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "emitter or inverted or slab" 2>&1 | tail -3
-} > gpurun_out/call06.log 2>&1
-tail -30 gpurun_out/call06.log
+echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+echo "== sweep"; timeout 600 python tools/sweep_variants.py --pairs 1:1 --scene dragon_bath 2>&1 | grep -v Warning
+timeout 600 python tools/sweep_variants.py --pairs 1:1 --scene dragon_bath --warm 400 2>&1 | grep -v Warning
+echo "== stage profile"; timeout 300 python tools/profile_step.py --warm 100 --steps 3 2>&1 | tail -3
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+echo "== bench"; SPH_BENCH_CPU_BUDGET_S=6 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r02_b.json 2> gpurun_out/bench_r02_b.err; tail -c 400 gpurun_out/bench_r02_b.err
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/bench_r02_b.json').read().strip().splitlines()[-1])
+for k in ('value','ms_per_step','steady','e2e','stage_ms'): print(k, json.dumps(d.get(k))[:300])
+print('extra', json.dumps(d['extra_configs'][0].get('ms_per_step')), json.dumps(d['extra_configs'][0].get('stage_ms')))
+P
+} > gpurun_out/call07.log 2>&1
+tail -40 gpurun_out/call07.log
