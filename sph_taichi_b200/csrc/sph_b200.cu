@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #endif
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -215,6 +216,34 @@ void bind_arrays(SphCtx *c) {
 inline RigidBodyDev *dev_bodies(SphCtx *c) { return reinterpret_cast<RigidBodyDev *>(c->ws + c->L.off_bodies); }
 
 inline int blocks_for(int64_t n, int t) { return (int)((n + t - 1) / t); }
+// Sharded steps: n is the capacity and the real counts are device state, so the step kernels run grid-stride /
+// tile loops on a grid of `per_sm` resident blocks per SM instead of one block per capacity slot (13 K idle blocks
+// per launch cost ~15 us each at 2 M live particles in a 3.8 M capacity).
+constexpr int kSMs = 148;
+inline int step_grid(const SphCtx *c, int64_t n, int t, int per_sm) {
+    const int full = blocks_for(n, t);
+    return c->P.slab_on ? std::min(full, kSMs * per_sm) : full;
+}
+
+// Launch with programmatic stream serialisation (the kernels of the step chain start with pdl_wait()): the next
+// kernel's blocks are scheduled while the previous grid drains, which removes most of the ~1.5 us gap per graph
+// node.  SPH_PDL=0 switches it off (A/B).
+#ifdef SPH_EMU
+#define PDL_LAUNCH(kern, grid, block, st, ...) kern<<<grid, block, 0, st>>>(__VA_ARGS__)
+#else
+const bool g_pdl = !(std::getenv("SPH_PDL") && std::atoi(std::getenv("SPH_PDL")) == 0);
+template <typename... KArgs, typename... Args>
+inline void pdl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#define PDL_LAUNCH(kern, grid, block, st, ...) pdl_launch(kern, dim3(grid), dim3(block), st, __VA_ARGS__)
+#endif
 
 void drop_graphs(SphCtx *c) {
     for (int k = 0; k < 2; ++k) {
@@ -249,14 +278,14 @@ int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *k
     if (tm) tm->mark(T_ZERO);
     CUDA_TRY(c, cudaMemsetAsync(c->ws + L.off_zero_begin, 0, L.off_zero_end - L.off_zero_begin, st));
     if (tm) tm->mark(T_HASH);
-    k_hash_count<<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
+    PDL_LAUNCH(k_hash_count, step_grid(c, P.n, 256, 8), 256, st, P, c->S);
     if (tm) tm->mark(T_SCAN);
-    k_scan<<<L.n_tiles, SCAN_THREADS, 0, st>>>(c->S.cell_end, P.C + 1, c->S.tile_state, c->S.tile_counter);
+    PDL_LAUNCH(k_scan, L.n_tiles, SCAN_THREADS, st, c->S.cell_end, P.C + 1, c->S.tile_state, c->S.tile_counter);
     if (tm) tm->mark(T_BUCKET);
-    k_bucket<<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
+    PDL_LAUNCH(k_bucket, step_grid(c, P.n, 256, 8), 256, st, P, c->S);
     if (tm) tm->mark(T_MOVE);
-    if (move_acc) k_rank_move<true><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
-    else k_rank_move<false><<<blocks_for(P.n, 256), 256, 0, st>>>(P, c->S);
+    if (move_acc) PDL_LAUNCH(k_rank_move<true>, step_grid(c, P.n, 256, 8), 256, st, P, c->S);
+    else PDL_LAUNCH(k_rank_move<false>, step_grid(c, P.n, 256, 8), 256, st, P, c->S);
     *kernels += 4;
     CUDA_TRY(c, cudaGetLastError());
     c->parity ^= 1;  // sorted state now lives in the other buffer set
@@ -269,17 +298,22 @@ int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *k
 // select the ablation variants (second dense loop for the density sum; separate advect kernel).
 void launch_pair_density(SphCtx *c, cudaStream_t st, int64_t *kernels) {
     const DevParams &P = c->P;
-    const int blocks = blocks_for(P.n, DENS_WARPS * 32);
-    if (c->var_density == 0) k_density_tma<false, false><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
-    else if (P.dfsph || c->var_density == 2) k_density_tma<true, false><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
-    else k_density_tma<true, true><<<blocks, DENS_WARPS * 32, 0, st>>>(P, c->S);
+    const int blocks = step_grid(c, P.n, DENS_WARPS * 32, DENS_MIN_BLOCKS);
+    if (c->var_density == 0) PDL_LAUNCH((k_density_tma<false, false>), blocks, DENS_WARPS * 32, st, P, c->S);
+    else if (P.dfsph || c->var_density == 2) PDL_LAUNCH((k_density_tma<true, false>), blocks, DENS_WARPS * 32, st, P, c->S);
+    else if (P.slab_on) PDL_LAUNCH((k_density_tma<true, true, true>), blocks, DENS_WARPS * 32, st, P, c->S);
+    else PDL_LAUNCH((k_density_tma<true, true>), blocks, DENS_WARPS * 32, st, P, c->S);
     *kernels += 1;
 }
 void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels, int split_mode = 0) {
     const DevParams &P = c->P;
     if (P.uniform_fluid && c->var_force != 0) {
-        k_force_packed<FORCE_BATCH, FORCE_THREADS, true><<<blocks_for(P.n, FORCE_THREADS), FORCE_THREADS, 0, st>>>(
-            P, c->S, split_mode);
+        if (P.slab_on)
+            PDL_LAUNCH((k_force_packed<FORCE_BATCH, FORCE_THREADS, true, true>), step_grid(c, P.n, FORCE_THREADS, FORCE_MIN_BLOCKS),
+                       FORCE_THREADS, st, P, c->S, split_mode);
+        else
+            PDL_LAUNCH((k_force_packed<FORCE_BATCH, FORCE_THREADS, true>), blocks_for(P.n, FORCE_THREADS), FORCE_THREADS, st, P, c->S,
+                       split_mode);
         *kernels += 1;
         if (tm) tm->mark(T_ADVECT);
         if (c->has_dynamic_solids && P.n_solid > 0) {

@@ -113,13 +113,19 @@ enum {
 };
 constexpr int SHARD_MIN_WIDTH = 5;  // a slab gives a layer away only while it is wider than this (ghost band 2 + send range 4 must fit)
 
-// Is record i an input of this step's classification?  (live records of the last sort + what the halo
-// exchange delivered behind them)
-__device__ __forceinline__ bool shard_input_valid(const DevParams &P, const int32_t *__restrict__ sd, int i) {
-    if (i < sd[SD_N_LIVE]) return true;
-    const int rl = P.n - 2 * P.halo_cap, rr = P.n - P.halo_cap;
-    return (i >= rl && i < rl + sd[SD_RECV_L]) || (i >= rr && i < rr + sd[SD_RECV_R]);
+// Sharded steps replay from a CUDA graph, so their grids are fixed while the record counts are device state:
+// the light kernels run grid-stride loops over a COMPACT input numbering -- u in [0, n_live + recv_l + recv_r) --
+// instead of launching one (mostly idle) thread per slot of the capacity.
+__device__ __forceinline__ int shard_input_total(const int32_t *__restrict__ sd) {
+    return sd[SD_N_LIVE] + sd[SD_RECV_L] + sd[SD_RECV_R];
 }
+__device__ __forceinline__ int shard_input_index(const DevParams &P, const int32_t *__restrict__ sd, int u) {
+    const int nl = sd[SD_N_LIVE], cl = sd[SD_RECV_L];
+    if (u < nl) return u;
+    if (u < nl + cl) return P.n - 2 * P.halo_cap + (u - nl);
+    return P.n - P.halo_cap + (u - nl - cl);
+}
+
 
 constexpr int NBR_CAP = 96;  // soak runs of the shipped scenes peak at 54 neighbours (tools/soak.py)
 constexpr int NBR_OVERFLOW = 0x7fffffff;

@@ -64,9 +64,14 @@ __global__ void k_upload_xv(DevParams P, DevArrays S, const float *x, const floa
 // (particle_system.py:311-375)
 // =====================================================================================
 __global__ void k_hash_count(DevParams P, DevArrays S) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    // sharded: the inputs are the live records of the last sort and what the halo exchange delivered
-    const bool active = i < P.n && (!P.slab_on || shard_input_valid(P, S.sd, i));
+    pdl_wait();
+    // sharded: the inputs are the live records of the last sort and what the halo exchange delivered (compact
+    // numbering, grid-stride loop: the grid of a graph-replayed step is fixed, the counts are device state)
+    const int total = P.slab_on ? shard_input_total(S.sd) : P.n;
+    for (int u0 = blockIdx.x * blockDim.x; u0 < total; u0 += gridDim.x * blockDim.x) {
+    const int u = u0 + threadIdx.x;
+    const bool active = u < total;
+    const int i = (P.slab_on && active) ? shard_input_index(P, S.sd, u) : u;
     int c = -1;
     if (active) {
         float4 p = S.posm[i];
@@ -116,6 +121,7 @@ __global__ void k_hash_count(DevParams P, DevArrays S) {
     if (active && lane == leader) base = atomicAdd(S.cell_end + c, __popc(peers));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (active) S.ticket[i] = base + __popc(peers & ((1u << lane) - 1u));
+    }
 }
 
 // ---- x-slab sharding: the per-step bookkeeping that used to live on the host (round 1: an all-gather of the
@@ -225,6 +231,7 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_IPT;  // one wave, at most two loo
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int32_t *__restrict__ data, int C,
                                                         unsigned long long *tile_state, int32_t *tile_counter) {
+    pdl_wait();
     __shared__ int s_tile;
     __shared__ int s_warp[SCAN_THREADS / 32];
     __shared__ int s_excl;
@@ -309,12 +316,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(int32_t *__restrict__ dat
 }
 
 __global__ void k_bucket(DevParams P, DevArrays S) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
-    if (P.slab_on && !shard_input_valid(P, S.sd, i)) return;
-    int c = S.cid[i];
-    int start = c > 0 ? S.cell_end[c - 1] : 0;
-    S.perm[start + S.ticket[i]] = i;
+    pdl_wait();
+    const int total = P.slab_on ? shard_input_total(S.sd) : P.n;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x) {
+        const int i = P.slab_on ? shard_input_index(P, S.sd, u) : u;
+        int c = S.cid[i];
+        int start = c > 0 ? S.cell_end[c - 1] : 0;
+        S.perm[start + S.ticket[i]] = i;
+    }
 }
 
 // The atomic tickets above give an arbitrary order inside a cell (as in the reference on a
@@ -323,9 +332,9 @@ __global__ void k_bucket(DevParams P, DevArrays S) {
 // arrays are bit-reproducible and identical to the oracle's.
 template <bool MOVE_ACC>
 __global__ void k_rank_move(DevParams P, DevArrays S) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.n) return;
-    if (P.slab_on && t >= S.cell_end[P.C]) return;  // sharded: P.n is the capacity, cell_end[C] the record count
+    pdl_wait();
+    const int total = P.slab_on ? S.cell_end[P.C] : P.n;  // sharded: P.n is the capacity, cell_end[C] the record count
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     int src = S.perm[t];
     int c = S.cid[src];
     int a = c > 0 ? S.cell_end[c - 1] : 0;
@@ -345,6 +354,7 @@ __global__ void k_rank_move(DevParams P, DevArrays S) {
     S.grid_ids[dst] = c;
     int sid = __float_as_int(misc.w);
     if (sid >= 0) S.solid_slot[sid] = dst;
+    }
 }
 
 // =====================================================================================
@@ -839,19 +849,23 @@ __device__ __forceinline__ uint32_t scan_chunk(const DevParams &P, const float4 
 #endif
 // FASTW (with INLINE_W): the branch-free spline_w_norm() with the 2k factor applied once per particle;
 // DFSPH keeps the reference's piecewise form (its solver loops count iterations against the oracle).
-template <bool INLINE_W, bool FASTW>
+// SHARD: the sharded step's instantiation (tile loop over a device-resident index range on a fixed grid); a
+// separate instantiation because the loop costs registers the single-GPU kernel does not have to spare.
+template <bool INLINE_W, bool FASTW, bool SHARD = false>
 __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tma(DevParams P, DevArrays S) {
+    pdl_wait();
     __shared__ __align__(128) float4 s_win[DENS_WARPS][2][WIN_CAP + 32];
     __shared__ __align__(8) uint64_t s_bar[DENS_WARPS][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (lane == 0) { mbar_init(&s_bar[warp][0], 1); mbar_init(&s_bar[warp][1], 1); }
     mbar_fence_init();
     __syncwarp();
+    uint32_t phase = 0u;  // bit b = parity of the next completion of barrier b (persists across the tiles of a block)
 
-    // sharded: owned particles + the first ghost layer per side (one index range; ghosts further out and the
-    // trash bucket are neighbours at most)
-    bool live = P.slab_on ? (i >= S.sd[SD_DENS0] && i < S.sd[SD_DENS1]) : i < P.n;
+    // one tile = blockDim.x consecutive particles starting at i - threadIdx.x; i_end bounds the particles that need
+    // a density
+    auto tile = [&](const int i, const int i_end) {
+    bool live = i < i_end;
     float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), mi = pi;
     uint32_t fl = 0;
     if (live) { pi = S.posm[i]; mi = S.misc[i]; fl = __float_as_uint(mi.z); }
@@ -886,7 +900,6 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
     };
     // warp-uniform window [J0, J1) and its staging into buffer b.  Returns 0 = empty, 1 = staged
     // (wait on the barrier), 2 = longer than WIN_CAP: scan global memory directly.
-    uint32_t phase = 0u;  // bit b = parity of the next completion of barrier b
     auto stage = [&](int j0, int j1, int b, int &J0, int &J1) -> int {
         bool ne = j1 > j0;
         J0 = __reduce_min_sync(0xffffffffu, ne ? j0 : 0x7fffffff);
@@ -1014,6 +1027,15 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
         S.fpv[2 * (size_t)i] = make_float4(pi.x, pi.y, pi.z, vol);
         S.fpv[2 * (size_t)i + 1] = make_float4(vb.x, vb.y, vb.z, dp);
     }
+    };  // tile
+    if (!SHARD) {
+        tile(blockIdx.x * blockDim.x + threadIdx.x, P.n);
+    } else {
+        // sharded (fixed grid of a graph-replayed step, device-resident counts): owned particles + the first ghost
+        // layer per side form ONE index range; ghosts further out and the trash bucket are neighbours at most
+        const int i0 = S.sd[SD_DENS0], i1 = S.sd[SD_DENS1];
+        for (int t0 = i0 + blockIdx.x * blockDim.x; t0 < i1; t0 += gridDim.x * blockDim.x) tile(t0 + threadIdx.x, i1);
+    }
 }
 
 // Fused force pass, general particle masses: 3 x 16 B gathered per neighbour.
@@ -1118,17 +1140,11 @@ __device__ __forceinline__ void force_pair_packed(const DevParams &P, const DevA
 // (k_shard_info), 2 = only the others, 0 = all -- the halo exchange of the NEXT step starts as soon as the
 // boundary particles are final and overlaps the interior.
 static_assert(LIST_PAD % FORCE_BATCH == 0 && NBR_CAP % LIST_PAD == 0, "list padding must cover a force batch");
-template <int B, int THREADS, bool FUSE_ADVECT>
+template <int B, int THREADS, bool FUSE_ADVECT, bool SHARD = false>
 __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevParams P, DevArrays S,
                                                                             int split_mode) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
-    if (split_mode) {
-        const int32_t *sd = S.sd;
-        bool boundary = (i >= sd[SD_SEND_L0] && i < sd[SD_SEND_L1]) || (i >= sd[SD_SEND_R0] && i < sd[SD_SEND_R1]);
-        if ((split_mode == 1) != boundary) return;
-    }
-    if (P.slab_on && i >= S.sd[SD_N_LIVE]) return;
+    pdl_wait();
+    auto one = [&](const int i) {
     float4 mi = S.misc[i];
     uint32_t fl = __float_as_uint(mi.z);
     if (!(fl & FLAG_FLUID)) return;
@@ -1191,6 +1207,23 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
         S.posm[i] = p;
         S.veld[i] = v;
     }
+    };  // one particle
+    if (!SHARD) {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < P.n) one(i);
+        return;
+    }
+    // sharded (fixed grid, device-resident ranges): the owned particles are ONE index range; the send ranges sit at
+    // its two ends (and may overlap in a narrow slab) -- every mode is at most two disjoint ranges
+    const int32_t *sd = S.sd;
+    const int l1 = sd[SD_SEND_L1], r0 = max(sd[SD_SEND_R0], l1);
+    int a0, a1, b0, b1;
+    if (split_mode == 1) { a0 = sd[SD_SEND_L0]; a1 = l1; b0 = r0; b1 = sd[SD_SEND_R1]; }
+    else if (split_mode == 2) { a0 = l1; a1 = r0; b0 = 0; b1 = 0; }
+    else { a0 = sd[SD_OWN0]; a1 = sd[SD_OWN1]; b0 = 0; b1 = 0; }
+    const int na = a1 - a0, total = na + (b1 - b0);
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x)
+        one(u < na ? a0 + u : b0 + (u - na));
 }
 
 // advect (WCSPH.py:143-149) for the dynamic SOLID particles only (companion of FUSE_ADVECT)

@@ -286,6 +286,7 @@ inline float rsqrt_ftz(float x) { return 1.0f / std::sqrt(x); }
 inline float rcp_ftz(float x) { return 1.0f / x; }
 inline void ldg256(const float4 *p, float4 &a, float4 &b) { a = p[0]; b = p[1]; }
 inline int ldg_stream(const int32_t *p) { return *p; }
+inline void pdl_wait() {}
 // mbarrier (arrival count 1): low word = completed phases, bits 32..62 = transaction count (signed: complete_tx may
 // run ahead of expect_tx), bit 63 = the arrive of the current phase has happened.  A phase completes when it has
 // arrived and its transaction count is zero.  Only the issuing lane writes; the waiting lanes poll.

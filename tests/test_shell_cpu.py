@@ -126,7 +126,7 @@ def test_argument_checks(fake_engine):
         _ps(sc).build_solver()
     ps = _ps(mixed_scene())
     n = ps.particle_max_num
-    with pytest.raises(ValueError, match="exceeds"):
+    with pytest.raises(ValueError, match="exceed particle_max_num"):
         ps.add_particles(0, 1, np.zeros((1, 3)), np.zeros((1, 3)), np.ones(1), np.zeros(1), np.ones(1), np.ones(1),
                          np.zeros((1, 3)))
     assert ps.particle_num[None] == n
@@ -158,3 +158,41 @@ def test_dfsph_host_loops(fake_engine):
     assert ops[0] == "dfsph:0" and ops[1] == "dfsph:1" and ops[-1] == "dfsph:10"
     assert "dfsph:8" in ops and "dfsph:9" in ops and "dfsph:7" in ops and "dfsph:3" in ops
     assert not s._fused_step_ok()
+
+
+def test_solver_attributes_drive_the_engine_constants(fake_engine):
+    """sph_base.py:13-21 / WCSPH.py:9-16: the reference bakes the SOLVER's attributes into its kernels; assigning
+    them (before a step) must reach the engine parameters here too, not be silently ignored."""
+    ps = _ps(mixed_scene())
+    solver = ps.build_solver()
+    eng = RecordingEngine.last
+    sent = []
+    eng.set_params = lambda p: sent.append(p)
+    solver.initialize()
+    n0 = len(sent)
+    solver.viscosity = 0.05
+    solver.surface_tension = 0.02
+    solver.stiffness = 40000.0
+    solver.step()
+    assert len(sent) == n0 + 1
+    p = sent[-1]
+    assert abs(p.viscosity - 0.05) < 1e-7 and abs(p.surface_tension - 0.02) < 1e-7 and abs(p.stiffness - 40000.0) < 1e-2
+    solver.step()
+    assert len(sent) == n0 + 1  # unchanged attributes: no re-push
+    solver.dt[None] = 2e-4
+    assert len(sent) == n0 + 2 and abs(sent[-1].dt - 2e-4) < 1e-9
+
+
+def test_emitter_reserve_extends_the_capacity(fake_engine):
+    sc = mixed_scene()
+    n_scene = _ps(mixed_scene()).particle_max_num
+    sc["Configuration"]["emitterReserve"] = 100
+    ps = _ps(sc)
+    assert ps.particle_max_num == n_scene + 100 and ps.particle_num[None] == n_scene
+    f0 = ps.fluid_particle_num
+    ps.add_particles(0, 100, np.full((100, 3), 0.3), np.zeros((100, 3)), np.full(100, 1000.0), np.zeros(100),
+                     np.ones(100), np.ones(100), np.zeros((100, 3)))
+    assert ps.particle_num[None] == n_scene + 100 and ps.fluid_particle_num == f0 + 100
+    with pytest.raises(ValueError, match="emitterReserve"):
+        ps.add_particles(0, 1, np.zeros((1, 3)), np.zeros((1, 3)), np.ones(1), np.zeros(1), np.ones(1), np.ones(1),
+                         np.zeros((1, 3)))

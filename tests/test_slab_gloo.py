@@ -47,8 +47,8 @@ def _run(nproc, port, extra):
 
 
 def test_sharded_two_ranks_equal_the_single_engine():
-    """Two emulated ranks over gloo: halo exchange every step, particles cross the cut (9 m/s for 24 steps)."""
-    out = _run(2, 29547, ["--counts", "24", "8", "8", "--steps", "24", "--vx", "9"])
+    """Two emulated ranks over gloo: halo exchange every step, particles cross the cut (12 m/s for 16 steps)."""
+    out = _run(2, 29547, ["--counts", "24", "8", "8", "--steps", "16", "--vx", "12"])
     assert out["ok"] and out["same_particle_set"] and out["max_dx_over_d"] < 1e-4, out
     assert out["migrated"] or out["cuts_moved"], out
     assert all(h > 0 for h in out["halo_bytes"]), out
@@ -57,7 +57,7 @@ def test_sharded_two_ranks_equal_the_single_engine():
 def test_three_ranks_skewed_cuts_are_rebalanced_on_the_device():
     """Deliberately skewed cuts, re-balancing every 2 steps: the cuts must move (decided on the device by both
     ranks of a cut from the exchanged headers), particles migrate, and the result still equals the single engine."""
-    out = _run(3, 29548, ["--counts", "32", "8", "8", "--steps", "40", "--vx", "6", "--skew", "-2", "--rebalance-every", "2"])
+    out = _run(3, 29548, ["--counts", "32", "8", "8", "--steps", "24", "--vx", "8", "--skew", "-2", "--rebalance-every", "2"])
     assert out["ok"] and out["same_particle_set"] and out["max_dx_over_d"] < 1e-4, out
     assert out["migrated"] and out["cuts_moved"], out
     first, last = out["owned_first_last"], None
