@@ -220,6 +220,7 @@ inline int blocks_for(int64_t n, int t) { return (int)((n + t - 1) / t); }
 // tile loops on a grid of `per_sm` resident blocks per SM instead of one block per capacity slot (13 K idle blocks
 // per launch cost ~15 us each at 2 M live particles in a 3.8 M capacity).
 constexpr int kSMs = 148;
+const bool g_shard_persistent = !(std::getenv("SPH_SHARD_PERSISTENT") && std::atoi(std::getenv("SPH_SHARD_PERSISTENT")) == 0);
 inline int step_grid(const SphCtx *c, int64_t n, int t, int per_sm) {
     const int full = blocks_for(n, t);
     return c->P.slab_on ? std::min(full, kSMs * per_sm) : full;
@@ -298,17 +299,18 @@ int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *k
 // select the ablation variants (second dense loop for the density sum; separate advect kernel).
 void launch_pair_density(SphCtx *c, cudaStream_t st, int64_t *kernels) {
     const DevParams &P = c->P;
-    const int blocks = step_grid(c, P.n, DENS_WARPS * 32, DENS_MIN_BLOCKS);
+    const bool persistent = P.slab_on && g_shard_persistent;
+    const int blocks = persistent ? step_grid(c, P.n, DENS_WARPS * 32, DENS_MIN_BLOCKS) : blocks_for(P.n, DENS_WARPS * 32);
     if (c->var_density == 0) PDL_LAUNCH((k_density_tma<false, false>), blocks, DENS_WARPS * 32, st, P, c->S);
     else if (P.dfsph || c->var_density == 2) PDL_LAUNCH((k_density_tma<true, false>), blocks, DENS_WARPS * 32, st, P, c->S);
-    else if (P.slab_on) PDL_LAUNCH((k_density_tma<true, true, true>), blocks, DENS_WARPS * 32, st, P, c->S);
+    else if (persistent) PDL_LAUNCH((k_density_tma<true, true, true>), blocks, DENS_WARPS * 32, st, P, c->S);
     else PDL_LAUNCH((k_density_tma<true, true>), blocks, DENS_WARPS * 32, st, P, c->S);
     *kernels += 1;
 }
 void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels, int split_mode = 0) {
     const DevParams &P = c->P;
     if (P.uniform_fluid && c->var_force != 0) {
-        if (P.slab_on)
+        if (P.slab_on && g_shard_persistent)
             PDL_LAUNCH((k_force_packed<FORCE_BATCH, FORCE_THREADS, true, true>), step_grid(c, P.n, FORCE_THREADS, FORCE_MIN_BLOCKS),
                        FORCE_THREADS, st, P, c->S, split_mode);
         else

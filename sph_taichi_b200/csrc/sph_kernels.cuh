@@ -864,8 +864,8 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
 
     // one tile = blockDim.x consecutive particles starting at i - threadIdx.x; i_end bounds the particles that need
     // a density
-    auto tile = [&](const int i, const int i_end) {
-    bool live = i < i_end;
+    auto tile = [&](const int i, const int i_begin, const int i_end) {
+    bool live = i >= i_begin && i < i_end;
     float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), mi = pi;
     uint32_t fl = 0;
     if (live) { pi = S.posm[i]; mi = S.misc[i]; fl = __float_as_uint(mi.z); }
@@ -1028,13 +1028,16 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
         S.fpv[2 * (size_t)i + 1] = make_float4(vb.x, vb.y, vb.z, dp);
     }
     };  // tile
-    if (!SHARD) {
-        tile(blockIdx.x * blockDim.x + threadIdx.x, P.n);
+    if (!SHARD) {  // (also the A/B fallback of sharded runs: one block per capacity tile)
+        tile(blockIdx.x * blockDim.x + threadIdx.x, P.slab_on ? S.sd[SD_DENS0] : 0, P.slab_on ? S.sd[SD_DENS1] : P.n);
     } else {
         // sharded (fixed grid of a graph-replayed step, device-resident counts): owned particles + the first ghost
         // layer per side form ONE index range; ghosts further out and the trash bucket are neighbours at most
+        // each block takes a CONTIGUOUS run of tiles: consecutive tiles share two thirds of their candidate windows
         const int i0 = S.sd[SD_DENS0], i1 = S.sd[SD_DENS1];
-        for (int t0 = i0 + blockIdx.x * blockDim.x; t0 < i1; t0 += gridDim.x * blockDim.x) tile(t0 + threadIdx.x, i1);
+        const long long tiles = ((long long)(i1 - i0) + blockDim.x - 1) / blockDim.x;
+        const int t_begin = (int)(tiles * blockIdx.x / gridDim.x), t_end = (int)(tiles * (blockIdx.x + 1) / gridDim.x);
+        for (int t = t_begin; t < t_end; ++t) tile(i0 + t * (int)blockDim.x + (int)threadIdx.x, i0, i1);
     }
 }
 
@@ -1208,9 +1211,16 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
         S.veld[i] = v;
     }
     };  // one particle
-    if (!SHARD) {
+    if (!SHARD) {  // (also the A/B fallback of sharded runs: one thread per capacity slot)
         const int i = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i < P.n) one(i);
+        if (i >= P.n) return;
+        if (P.slab_on) {
+            const int32_t *sd = S.sd;
+            if (i < sd[SD_OWN0] || i >= sd[SD_OWN1]) return;
+            const bool boundary = (i >= sd[SD_SEND_L0] && i < sd[SD_SEND_L1]) || (i >= sd[SD_SEND_R0] && i < sd[SD_SEND_R1]);
+            if (split_mode && (split_mode == 1) != boundary) return;
+        }
+        one(i);
         return;
     }
     // sharded (fixed grid, device-resident ranges): the owned particles are ONE index range; the send ranges sit at
@@ -1222,8 +1232,13 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
     else if (split_mode == 2) { a0 = l1; a1 = r0; b0 = 0; b1 = 0; }
     else { a0 = sd[SD_OWN0]; a1 = sd[SD_OWN1]; b0 = 0; b1 = 0; }
     const int na = a1 - a0, total = na + (b1 - b0);
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x)
-        one(u < na ? a0 + u : b0 + (u - na));
+    // contiguous run of tiles per block (neighbouring particles gather the same records: L1 reuse)
+    const long long tiles = ((long long)total + blockDim.x - 1) / blockDim.x;
+    const int t_begin = (int)(tiles * blockIdx.x / gridDim.x), t_end = (int)(tiles * (blockIdx.x + 1) / gridDim.x);
+    for (int t = t_begin; t < t_end; ++t) {
+        const int u = t * (int)blockDim.x + (int)threadIdx.x;
+        if (u < total) one(u < na ? a0 + u : b0 + (u - na));
+    }
 }
 
 // advect (WCSPH.py:143-149) for the dynamic SOLID particles only (companion of FUSE_ADVECT)
