@@ -216,11 +216,11 @@ void bind_arrays(SphCtx *c) {
 inline RigidBodyDev *dev_bodies(SphCtx *c) { return reinterpret_cast<RigidBodyDev *>(c->ws + c->L.off_bodies); }
 
 inline int blocks_for(int64_t n, int t) { return (int)((n + t - 1) / t); }
-// Sharded steps: n is the capacity and the real counts are device state, so the step kernels run grid-stride /
-// tile loops on a grid of `per_sm` resident blocks per SM instead of one block per capacity slot (13 K idle blocks
-// per launch cost ~15 us each at 2 M live particles in a 3.8 M capacity).
+// Sharded steps: n is the capacity and the real counts are device state, so the LIGHT step kernels (histogram,
+// bucket, rank + move) run grid-stride loops over the compact input numbering on a grid of `per_sm` resident blocks
+// per SM instead of one thread per capacity slot (sort chain 0.121 -> 0.106 ms at 2 M particles per rank); the pair
+// kernels keep one block per tile.
 constexpr int kSMs = 148;
-const bool g_shard_persistent = !(std::getenv("SPH_SHARD_PERSISTENT") && std::atoi(std::getenv("SPH_SHARD_PERSISTENT")) == 0);
 inline int step_grid(const SphCtx *c, int64_t n, int t, int per_sm) {
     const int full = blocks_for(n, t);
     return c->P.slab_on ? std::min(full, kSMs * per_sm) : full;
@@ -299,23 +299,17 @@ int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *k
 // select the ablation variants (second dense loop for the density sum; separate advect kernel).
 void launch_pair_density(SphCtx *c, cudaStream_t st, int64_t *kernels) {
     const DevParams &P = c->P;
-    const bool persistent = P.slab_on && g_shard_persistent;
-    const int blocks = persistent ? step_grid(c, P.n, DENS_WARPS * 32, DENS_MIN_BLOCKS) : blocks_for(P.n, DENS_WARPS * 32);
+    const int blocks = blocks_for(P.n, DENS_WARPS * 32);
     if (c->var_density == 0) PDL_LAUNCH((k_density_tma<false, false>), blocks, DENS_WARPS * 32, st, P, c->S);
     else if (P.dfsph || c->var_density == 2) PDL_LAUNCH((k_density_tma<true, false>), blocks, DENS_WARPS * 32, st, P, c->S);
-    else if (persistent) PDL_LAUNCH((k_density_tma<true, true, true>), blocks, DENS_WARPS * 32, st, P, c->S);
     else PDL_LAUNCH((k_density_tma<true, true>), blocks, DENS_WARPS * 32, st, P, c->S);
     *kernels += 1;
 }
 void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels, int split_mode = 0) {
     const DevParams &P = c->P;
     if (P.uniform_fluid && c->var_force != 0) {
-        if (P.slab_on && g_shard_persistent)
-            PDL_LAUNCH((k_force_packed<FORCE_BATCH, FORCE_THREADS, true, true>), step_grid(c, P.n, FORCE_THREADS, FORCE_MIN_BLOCKS),
-                       FORCE_THREADS, st, P, c->S, split_mode);
-        else
-            PDL_LAUNCH((k_force_packed<FORCE_BATCH, FORCE_THREADS, true>), blocks_for(P.n, FORCE_THREADS), FORCE_THREADS, st, P, c->S,
-                       split_mode);
+        PDL_LAUNCH((k_force_packed<FORCE_BATCH, FORCE_THREADS, true>), blocks_for(P.n, FORCE_THREADS), FORCE_THREADS, st, P, c->S,
+                   split_mode);
         *kernels += 1;
         if (tm) tm->mark(T_ADVECT);
         if (c->has_dynamic_solids && P.n_solid > 0) {

@@ -849,9 +849,7 @@ __device__ __forceinline__ uint32_t scan_chunk(const DevParams &P, const float4 
 #endif
 // FASTW (with INLINE_W): the branch-free spline_w_norm() with the 2k factor applied once per particle;
 // DFSPH keeps the reference's piecewise form (its solver loops count iterations against the oracle).
-// SHARD: the sharded step's instantiation (tile loop over a device-resident index range on a fixed grid); a
-// separate instantiation because the loop costs registers the single-GPU kernel does not have to spare.
-template <bool INLINE_W, bool FASTW, bool SHARD = false>
+template <bool INLINE_W, bool FASTW>
 __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tma(DevParams P, DevArrays S) {
     pdl_wait();
     __shared__ __align__(128) float4 s_win[DENS_WARPS][2][WIN_CAP + 32];
@@ -1028,17 +1026,10 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
         S.fpv[2 * (size_t)i + 1] = make_float4(vb.x, vb.y, vb.z, dp);
     }
     };  // tile
-    if (!SHARD) {  // (also the A/B fallback of sharded runs: one block per capacity tile)
-        tile(blockIdx.x * blockDim.x + threadIdx.x, P.slab_on ? S.sd[SD_DENS0] : 0, P.slab_on ? S.sd[SD_DENS1] : P.n);
-    } else {
-        // sharded (fixed grid of a graph-replayed step, device-resident counts): owned particles + the first ghost
-        // layer per side form ONE index range; ghosts further out and the trash bucket are neighbours at most
-        // each block takes a CONTIGUOUS run of tiles: consecutive tiles share two thirds of their candidate windows
-        const int i0 = S.sd[SD_DENS0], i1 = S.sd[SD_DENS1];
-        const long long tiles = ((long long)(i1 - i0) + blockDim.x - 1) / blockDim.x;
-        const int t_begin = (int)(tiles * blockIdx.x / gridDim.x), t_end = (int)(tiles * (blockIdx.x + 1) / gridDim.x);
-        for (int t = t_begin; t < t_end; ++t) tile(i0 + t * (int)blockDim.x + (int)threadIdx.x, i0, i1);
-    }
+    // sharded steps: the grid covers the capacity (the hardware block scheduler balances better than a persistent
+    // tile loop: 0.385 vs 0.49 ms at 2 M particles per rank, profiles/r02_shard_timing.txt); only owned particles
+    // + the first ghost layer per side -- one index range of the device-resident step state -- need a density
+    tile(blockIdx.x * blockDim.x + threadIdx.x, P.slab_on ? S.sd[SD_DENS0] : 0, P.slab_on ? S.sd[SD_DENS1] : P.n);
 }
 
 // Fused force pass, general particle masses: 3 x 16 B gathered per neighbour.
@@ -1143,7 +1134,7 @@ __device__ __forceinline__ void force_pair_packed(const DevParams &P, const DevA
 // (k_shard_info), 2 = only the others, 0 = all -- the halo exchange of the NEXT step starts as soon as the
 // boundary particles are final and overlaps the interior.
 static_assert(LIST_PAD % FORCE_BATCH == 0 && NBR_CAP % LIST_PAD == 0, "list padding must cover a force batch");
-template <int B, int THREADS, bool FUSE_ADVECT, bool SHARD = false>
+template <int B, int THREADS, bool FUSE_ADVECT>
 __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevParams P, DevArrays S,
                                                                             int split_mode) {
     pdl_wait();
@@ -1211,34 +1202,15 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
         S.veld[i] = v;
     }
     };  // one particle
-    if (!SHARD) {  // (also the A/B fallback of sharded runs: one thread per capacity slot)
-        const int i = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i >= P.n) return;
-        if (P.slab_on) {
-            const int32_t *sd = S.sd;
-            if (i < sd[SD_OWN0] || i >= sd[SD_OWN1]) return;
-            const bool boundary = (i >= sd[SD_SEND_L0] && i < sd[SD_SEND_L1]) || (i >= sd[SD_SEND_R0] && i < sd[SD_SEND_R1]);
-            if (split_mode && (split_mode == 1) != boundary) return;
-        }
-        one(i);
-        return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    if (P.slab_on) {  // sharded: owned particles only, split into the send ranges and the rest
+        const int32_t *sd = S.sd;
+        if (i < sd[SD_OWN0] || i >= sd[SD_OWN1]) return;
+        const bool boundary = (i >= sd[SD_SEND_L0] && i < sd[SD_SEND_L1]) || (i >= sd[SD_SEND_R0] && i < sd[SD_SEND_R1]);
+        if (split_mode && (split_mode == 1) != boundary) return;
     }
-    // sharded (fixed grid, device-resident ranges): the owned particles are ONE index range; the send ranges sit at
-    // its two ends (and may overlap in a narrow slab) -- every mode is at most two disjoint ranges
-    const int32_t *sd = S.sd;
-    const int l1 = sd[SD_SEND_L1], r0 = max(sd[SD_SEND_R0], l1);
-    int a0, a1, b0, b1;
-    if (split_mode == 1) { a0 = sd[SD_SEND_L0]; a1 = l1; b0 = r0; b1 = sd[SD_SEND_R1]; }
-    else if (split_mode == 2) { a0 = l1; a1 = r0; b0 = 0; b1 = 0; }
-    else { a0 = sd[SD_OWN0]; a1 = sd[SD_OWN1]; b0 = 0; b1 = 0; }
-    const int na = a1 - a0, total = na + (b1 - b0);
-    // contiguous run of tiles per block (neighbouring particles gather the same records: L1 reuse)
-    const long long tiles = ((long long)total + blockDim.x - 1) / blockDim.x;
-    const int t_begin = (int)(tiles * blockIdx.x / gridDim.x), t_end = (int)(tiles * (blockIdx.x + 1) / gridDim.x);
-    for (int t = t_begin; t < t_end; ++t) {
-        const int u = t * (int)blockDim.x + (int)threadIdx.x;
-        if (u < total) one(u < na ? a0 + u : b0 + (u - na));
-    }
+    one(i);
 }
 
 // advect (WCSPH.py:143-149) for the dynamic SOLID particles only (companion of FUSE_ADVECT)

@@ -326,7 +326,8 @@ class ParticleSystem:
         lattice, verts, faces = rigid_body_lattice(rigid_body, self.particle_diameter, self.cfg.scene_dir)
         if verts is not None:
             rigid_body["restPosition"] = verts
-            rigid_body["restCenterOfMass"] = verts.mean(axis=0)
+            from .voxelizer import vertex_mean
+            rigid_body["restCenterOfMass"] = vertex_mean(verts, rigid_body.get("_vertexWeights"))
             rigid_body["meshFaces"] = faces
         return lattice.astype(np.float64) * self.particle_diameter
 

@@ -231,8 +231,9 @@ def rigid_body_lattice(body, diameter, scene_dir):
         cands += [geom, os.path.join(scene_dir, geom), os.path.join(scene_dir, "..", "..", geom)]
     for path in cands:
         if os.path.isfile(path):
-            idx, verts, faces = voxelizer.voxelize_rigid_body(
+            idx, verts, faces, weights = voxelizer.voxelize_rigid_body(
                 path, body["scale"], body["rotationAngle"], body["rotationAxis"], body["translation"], diameter)
+            body["_vertexWeights"] = weights  # trimesh's vertex multiplicity (rest centre of mass, voxelizer.load_obj)
             return idx, verts, faces
     fix = body.get("voxelizedPointsFile")
     if fix:
@@ -295,7 +296,7 @@ def assemble_particles(cfg, dim, diameter, verbose=False):
         body["voxelizedPoints"] = pts64
         if verts is not None:
             body["restPosition"] = verts
-            body["restCenterOfMass"] = verts.mean(axis=0)
+            body["restCenterOfMass"] = voxelizer.vertex_mean(verts, body.get("_vertexWeights"))
             body["meshFaces"] = faces
         object_collection[body["objectId"]] = body
         rigid_ids.add(body["objectId"])

@@ -252,7 +252,7 @@ class ShardedSimulation:
             torch.cuda.synchronize(self.device)
 
 
-def build_sharded(scene_dict, rank, world, device, group=None, capacity_factor=1.35, rebalance_every=8, slabs=None,
+def build_sharded(scene_dict, rank, world, device, group=None, capacity_factor=1.2, rebalance_every=8, slabs=None,
                   transport=None):
     """Assemble the scene on every rank, plan the slabs from the initial layer histogram and load this rank's
     share into a CUDA engine.  Returns (ShardedSimulation, n_total)."""

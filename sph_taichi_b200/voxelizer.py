@@ -28,23 +28,52 @@ from scipy import ndimage
 REFERENCE_PI = 3.1415926  # particle_system.py:427
 
 
-def load_obj(path):
-    """Minimal Wavefront OBJ reader: returns (vertices float64 [V,3], faces int64 [F,3])."""
-    verts = []
-    faces = []
+def load_obj(path, with_multiplicity=False):
+    """Minimal Wavefront OBJ reader: returns (vertices float64 [V,3], faces int64 [F,3]).
+
+    ``with_multiplicity=True`` also returns, per vertex, how many copies of it trimesh's loader keeps: trimesh splits
+    a vertex per distinct (position, uv, normal) VALUE combination it is used with (``unmerge_faces`` on the index
+    triples, then ``merge_vertices`` by value with ``merge_tex = merge_norm = False``) and drops vertices no face
+    references, so ``mesh.vertices.mean()`` -- the pivot of the reference's rotation and its rest centre of mass
+    (particle_system.py:428, 436) -- is this weighted mean.  For both meshes the reference ships every vertex has
+    exactly one uv / normal value (weights all 1: tests/test_voxelizer.py); restated from trimesh's source from
+    memory, the package is not installable offline."""
+    verts, uvs, normals = [], [], []
+    faces, corners = [], []
     with open(path, "r") as fh:
         for line in fh:
             if line.startswith("v "):
                 p = line.split()
                 verts.append((float(p[1]), float(p[2]), float(p[3])))
+            elif line.startswith("vt "):
+                uvs.append(tuple(float(t) for t in line.split()[1:3]))
+            elif line.startswith("vn "):
+                normals.append(tuple(float(t) for t in line.split()[1:4]))
             elif line.startswith("f "):
-                idx = [int(tok.split("/")[0]) for tok in line.split()[1:]]
+                toks = [tok.split("/") for tok in line.split()[1:]]
+                idx = [int(t[0]) for t in toks]
                 for k in range(1, len(idx) - 1):  # fan-triangulate polygons
                     faces.append((idx[0], idx[k], idx[k + 1]))
+                if with_multiplicity:
+                    corners.extend(toks)
     v = np.asarray(verts, dtype=np.float64)
     f = np.asarray(faces, dtype=np.int64)
     f = np.where(f < 0, f + len(v), f - 1)  # OBJ is 1-based; negatives are relative
-    return v, f
+    if not with_multiplicity:
+        return v, f
+
+    def pick(table, tok):
+        if tok is None or tok == "" or not table:
+            return None
+        k = int(tok)
+        return table[k - 1 if k > 0 else k]
+
+    combos = [set() for _ in range(len(v))]
+    for t in corners:
+        k = int(t[0])
+        vi = k - 1 if k > 0 else len(v) + k
+        combos[vi].add((pick(uvs, t[1] if len(t) > 1 else None), pick(normals, t[2] if len(t) > 2 else None)))
+    return v, f, np.asarray([len(c) for c in combos], dtype=np.float64)
 
 
 def rotation_about_point(angle, axis, point):
@@ -64,11 +93,20 @@ def rotation_about_point(angle, axis, point):
     return M
 
 
-def transform_rigid_mesh(vertices, scale, rotation_angle_deg, rotation_axis, translation):
+def vertex_mean(vertices, weights=None):
+    """``mesh.vertices.mean(axis=0)`` of the trimesh mesh (see ``load_obj``: vertices weighted by their copies)."""
+    v = np.asarray(vertices, dtype=np.float64)
+    if weights is None:
+        return v.mean(axis=0)
+    w = np.asarray(weights, dtype=np.float64)
+    return (v * w[:, None]).sum(axis=0) / w.sum()
+
+
+def transform_rigid_mesh(vertices, scale, rotation_angle_deg, rotation_axis, translation, weights=None):
     """Scale, rotate about the vertex mean, translate (particle_system.py:424-431)."""
     v = np.asarray(vertices, dtype=np.float64) * np.asarray(scale, dtype=np.float64)
     angle = rotation_angle_deg / 360 * 2 * REFERENCE_PI
-    M = rotation_about_point(angle, rotation_axis, v.mean(axis=0))
+    M = rotation_about_point(angle, rotation_axis, vertex_mean(v, weights))
     v = v @ M[:3, :3].T + M[:3, 3]
     return v + np.asarray(translation, dtype=np.float64)
 
@@ -120,8 +158,8 @@ def voxelize_solid(vertices, faces, pitch):
 def voxelize_rigid_body(path, scale, rotation_angle_deg, rotation_axis, translation, pitch):
     """Full reference pipeline for one ``RigidBodies`` entry.
 
-    Returns ``(lattice_idx int64 [M,3], transformed_vertices, faces)``.
+    Returns ``(lattice_idx int64 [M,3], transformed_vertices, faces, vertex_weights)``.
     """
-    v, f = load_obj(path)
-    v = transform_rigid_mesh(v, scale, rotation_angle_deg, rotation_axis, translation)
-    return voxelize_solid(v, f, pitch), v, f
+    v, f, w = load_obj(path, with_multiplicity=True)
+    v = transform_rigid_mesh(v, scale, rotation_angle_deg, rotation_axis, translation, weights=w)
+    return voxelize_solid(v, f, pitch), v, f, w

@@ -109,3 +109,27 @@ def test_named_scenes_match_the_reference_scene_files():
             for x, y in zip(a, b):
                 y = {k: v for k, v in y.items() if k != "voxelizedPointsFile"}
                 assert x == y, (name, key)
+
+
+def test_obj_vertex_multiplicity_follows_trimesh():
+    """trimesh keeps one copy of a vertex per distinct (uv, normal) value it is used with and drops unreferenced
+    vertices; the rotation pivot and the rest centre of mass of the reference are the mean over THOSE vertices
+    (particle_system.py:428, 436).  A seam vertex counts twice; both meshes the reference ships have weight 1
+    everywhere, so for them the plain mean is the trimesh mean (and the committed fixtures stay valid)."""
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "seam.obj")
+        with open(path, "w") as fh:
+            fh.write("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nv 9 9 9\n")          # vertex 5 is unreferenced
+            fh.write("vt 0 0\nvt 1 0\nvt 0 1\nvt 0.5 0.5\n")
+            fh.write("f 1/1 2/2 3/3\nf 2/4 4/1 3/3\n")                           # vertex 2 is used with two uv values
+        v, f, w = vx.load_obj(path, with_multiplicity=True)
+        assert f.shape == (2, 3) and list(w) == [1, 2, 1, 1, 0]
+        assert np.allclose(vx.vertex_mean(v, w), (v[0] + 2 * v[1] + v[2] + v[3]) / 5)
+        moved = vx.transform_rigid_mesh(v, [1, 1, 1], 90, [0, 0, 1], [0, 0, 0], weights=w)
+        pivot = vx.vertex_mean(v, w)
+        assert np.allclose(vx.vertex_mean(moved, w), pivot)                       # the weighted mean is the fixed point
+    ref = "/root/reference/data/models"
+    if os.path.isdir(ref):
+        for name in ("armadillo_small.obj", "Dragon_50k.obj"):
+            v, f, w = vx.load_obj(os.path.join(ref, name), with_multiplicity=True)
+            assert (w == 1).all(), name

@@ -1,13 +1,18 @@
 #!/bin/bash
-# Round-2 GPU call 11 (2 GPUs): persistent (contiguous tile runs) vs one-block-per-capacity-tile pair kernels in sharded steps.
+# Round-2 GPU call 12 (4 GPUs): sharded engine at N = 4 (box_4m): parity, timing, bench line.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port $1 tools/shard_timing.py "${@:2}" 2>&1 | grep "^{"; }
+N=4
 {
-echo "== persistent (contiguous runs), cap 1.35"; run 29541 --tag pers
-echo "== persistent, cap 1.15"; run 29542 --tag pers-cap1.15 --capacity 1.15
-echo "== one block per tile, cap 1.35"; SPH_SHARD_PERSISTENT=0 run 29543 --tag plain
-echo "== one block per tile, cap 1.15"; SPH_SHARD_PERSISTENT=0 run 29544 --tag plain-cap1.15 --capacity 1.15
-echo "== parity (persistent)"; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29534 tools/check_slab_parity.py --counts 128 48 48 --steps 120 --rebalance-every 4 2>&1 | grep "^{" | cut -c1-230
-} > gpurun_out/call11.log 2>&1
-tail -30 gpurun_out/call11.log
+echo "== parity $N ranks"; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port 29534 tools/check_slab_parity.py --counts 160 48 48 --steps 120 --rebalance-every 4 2>&1 | grep "^{" | cut -c1-400
+echo "== timing"; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port 29541 tools/shard_timing.py --tag n$N 2>&1 | grep "^{"
+echo "== bench --gpus $N"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port 29535 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_r02_n$N.json 2> gpurun_out/bench_r02_n$N.err; tail -c 600 gpurun_out/bench_r02_n$N.err; python - <<P
+import json
+try:
+    d=json.loads(open('gpurun_out/bench_r02_n$N.json').read().strip().splitlines()[-1])
+    for k in ('value','ms_per_step','parity_check','strong_scaling','halo','stage_ms_slowest_rank','e2e','sharding'): print(k, json.dumps(d.get(k))[:400])
+except Exception as e: print("bench parse failed", e, open('gpurun_out/bench_r02_n$N.json').read()[-800:])
+P
+} > gpurun_out/call12.log 2>&1
+tail -30 gpurun_out/call12.log

@@ -28,12 +28,12 @@ def main():
         pitch = 2.0 * sc["Configuration"]["particleRadius"]
         for body in sc["RigidBodies"]:
             mesh = os.path.join(ref, body["geometryFile"])
-            idx, verts, _ = voxelizer.voxelize_rigid_body(
+            idx, verts, _, weights = voxelizer.voxelize_rigid_body(
                 mesh, body["scale"], body["rotationAngle"], body["rotationAxis"], body["translation"], pitch)
             assert np.abs(idx).max() < 32767
             dst = os.path.join(out, os.path.basename(body["voxelizedPointsFile"]))
             np.savez_compressed(dst, lattice=idx.astype(np.int16), pitch=np.float64(pitch),
-                                rest_center_of_mass=verts.mean(axis=0))
+                                rest_center_of_mass=voxelizer.vertex_mean(verts, weights))
             print(f"{name} body {body['objectId']}: {idx.shape[0]} voxels -> {dst}")
 
 

@@ -13,7 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scene", default="box_4m")
 ap.add_argument("--steps", type=int, default=50)
 ap.add_argument("--warm", type=int, default=30)
-ap.add_argument("--capacity", type=float, default=1.35)
+ap.add_argument("--capacity", type=float, default=1.2)
 ap.add_argument("--tag", default="")
 a = ap.parse_args()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
