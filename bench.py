@@ -105,22 +105,56 @@ def roofline_entry(kind, workload, n, launch_ms, total_ms, peak, work, sm_mhz):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs.
+
+    In-process NVML (pynvml) from a thread, one cheap query pair every 10 ms: `nvidia-smi -lms 20` as a child process
+    stalled the sampled GPU for milliseconds per poll -- invisible in a 4 s region, but +46 % on the 10 ms timed
+    region of a sharded run (profiles/r02_shard_timing.txt).  Falls back to `nvidia-smi -lms 100` without pynvml."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index=0):
-        self.rows = []
-        self.proc = None
+        self.rows, self.sm, self.reasons = [], [], set()
+        self.proc = self.thread = self.nvml = None
         self.index = index
+        self.max_mhz = None
+        self._stop = threading.Event()
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = (pynvml, h)
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        for name, bit in self.BITS.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    self._stop.wait(0.010)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            time.sleep(1.0)  # nvidia-smi's start-up (NVML init, enumeration) must not fall into the timed region
         except Exception:
             self.proc = None
 
@@ -129,6 +163,12 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=1.0)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "reasons": sorted(self.reasons), "source": "NVML in-process, 10 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -148,7 +188,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 def best_thread_count(o, reps=3):

@@ -15,6 +15,8 @@ ap.add_argument("--steps", type=int, default=50)
 ap.add_argument("--warm", type=int, default=30)
 ap.add_argument("--capacity", type=float, default=1.2)
 ap.add_argument("--tag", default="")
+ap.add_argument("--pre-parity", action="store_true", help="gather + single-GPU engine on rank 0 first (what bench.py does)")
+ap.add_argument("--sampler", action="store_true", help="run the nvidia-smi clock sampler during the timed steps")
 a = ap.parse_args()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dev = torch.device(f"cuda:{int(os.environ['LOCAL_RANK'])}")
@@ -22,9 +24,26 @@ torch.cuda.set_device(dev)
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 sim, n_total = slab.build_sharded(scene.NAMED_SCENES[a.scene](), rank, world, dev, capacity_factor=a.capacity)
 sim.step(a.warm)
+if a.pre_parity:
+    from sph_taichi_b200 import ParticleSystem, SimConfig
+    g = slab.gather_owned(sim)
+    if rank == 0:
+        ps = ParticleSystem(SimConfig(scene.NAMED_SCENES[a.scene]()), device=dev)
+        sv = ps.build_solver(); sv.initialize(); sv.step(a.warm)
+        print("parity", slab.compare_with_single(g, ps, 0.02), flush=True)
+        del sv, ps, g
+        torch.cuda.empty_cache()
+    flag = torch.tensor([1], device=dev); dist.broadcast(flag, src=0)
+    sim.step(3)
 torch.cuda.synchronize(); dist.barrier()
+sampler = None
+if a.sampler and rank == 0:
+    import bench
+    sampler = bench.ClockSampler(int(os.environ["LOCAL_RANK"])); sampler.start()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); sim.step(a.steps); e1.record(); torch.cuda.synchronize()
+if sampler:
+    print("clocks", sampler.stop(), flush=True)
 ms = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 acc = {}
