@@ -116,21 +116,28 @@ class ClockSampler:
     BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index=0):
+        """Construct EARLY (before the warm-up): nvmlInit enumerates the devices and stalls them for ~100 ms -- it must
+        not fall into the timed region (it did: 3.3 instead of 0.78 ms/step over a 16 ms region)."""
         self.rows, self.sm, self.reasons = [], [], set()
         self.proc = self.thread = self.nvml = None
         self.index = index
         self.max_mhz = None
         self._stop = threading.Event()
-
-    def start(self):
         try:
             import pynvml
             pynvml.nvmlInit()
             visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
             h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)  # first query outside the timed region too
             self.nvml = (pynvml, h)
+        except Exception:
+            self.nvml = None
+
+    def start(self):
+        if self.nvml is not None:
+            pynvml, h = self.nvml
 
             def poll():
                 while not self._stop.is_set():
@@ -147,8 +154,6 @@ class ClockSampler:
             self.thread = threading.Thread(target=poll, daemon=True)
             self.thread.start()
             return
-        except Exception:
-            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -322,6 +327,8 @@ def run_single(args):
     BAD = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     for attempt in range(2):  # a run that saw a thermal / hw slowdown is rejected and re-measured once
         sampler = ClockSampler(0)
+        solver.step(3)
+        torch.cuda.synchronize()
         sampler.start()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         launches0 = eng.launch_count()

@@ -168,13 +168,13 @@ int sph_dfsph_op(SphCtx *ctx, int32_t op, float arg, void *out_dev, void *stream
  * particle_system.py:292-294: after the sort every layer is ONE contiguous index range) and keeps
  * `ghost_layers` (2) layers of copies of its neighbours' particles, so ONE exchange per step suffices.
  * Everything a step needs lives on the device -- live count, slab bounds, send / receive ranges, record counts
- * (carried in-band in a header) -- so a whole sharded step replays from one CUDA graph:
+ * (carried in-band in a header) -- so a whole sharded step is a fixed launch sequence (capturable as ONE CUDA graph):
  *
  *     plan (receive counts, cut re-balancing) -> classify + sort -> info (send ranges) -> density ->
  *     forces + integration of the boundary particles -> pack -> { halo exchange of the NEXT step  ||
  *     forces + integration of the interior }
  *
- * and the host only launches graphs.  Every record is classified as owned / ghost / dropped from its position
+ * and the host only launches.  Every record is classified as owned / ghost / dropped from its position
  * alone (both ranks evaluate the same fp32 expression), so migration needs no extra message; cuts move by at
  * most one layer every `rebalance_every` steps, decided identically on both sides of a cut from the owned
  * counts in the headers.  Fluid-only scenes with one fluid (uniform masses); rigid bodies are single-GPU.
@@ -199,7 +199,8 @@ int sph_shard_configure(SphCtx *ctx, int32_t x_lo, int32_t x_hi, int32_t ghost_l
                         int32_t rebalance_every);
 /* first sort of the packed particles + the first halo exchange (no physics) */
 int sph_shard_begin(SphCtx *ctx, void *stream);
-/* nsteps sharded SPHBase.step()s (sph_base.py:263-271), one CUDA-graph replay per step */
+/* nsteps sharded SPHBase.step()s (sph_base.py:263-271): asynchronous launches that run ahead of the device (no host
+ * synchronisation inside a step); SPH_SHARD_GRAPH=1 replays one captured CUDA graph per step instead */
 int sph_shard_step(SphCtx *ctx, int32_t nsteps, void *stream);
 /* the exchange alone: sends the packed staging, receives behind the live records */
 int sph_halo_exchange(SphCtx *ctx, void *stream);

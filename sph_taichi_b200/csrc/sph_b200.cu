@@ -944,7 +944,12 @@ int sph_shard_step(SphCtx *ctx, int32_t nsteps, void *stream) {
     if (nsteps < 0) return SPH_E_ARG;
     if (!ctx->shard_begun) return fail(ctx, SPH_E_ARG, "sph_shard_begin was not called");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static const bool eager = std::getenv("SPH_SHARD_NO_GRAPH") != nullptr;  // debugging aid: launch every step un-graphed
+    // Un-graphed launches are the DEFAULT here: nothing in a sharded step waits for the host any more, so the launches
+    // run ahead of the device, and a graph replay -- whose two branches (exchange || interior forces) must both finish
+    // before the next replay may start -- measured 9-12 % SLOWER (0.779 vs 0.712 ms per step at 2 x 2 M particles,
+    // 0.51 vs 0.45 at 4 x 1 M; profiles/r02_shard_timing.txt).  SPH_SHARD_GRAPH=1 replays the captured graph instead
+    // (one graph per ping-pong parity and exchange width; pays off for small per-rank problems).
+    static const bool eager = !(std::getenv("SPH_SHARD_GRAPH") && std::atoi(std::getenv("SPH_SHARD_GRAPH")) != 0);
     for (int s = 0; s < nsteps; ++s) {
         const bool wide = shard_wide(ctx);
         if (eager) {

@@ -9,9 +9,10 @@ The reference is single-device; this is the multi-GPU extension BASELINE.json as
   recomputed locally from the second, and a SINGLE exchange per step is enough.
 * The whole sharded step lives in ``libsph_b200.so`` (``sph_shard_*``, include/sph_b200.h): live counts, slab
   bounds, send / receive ranges and the record counts (in-band headers) are DEVICE state, the exchange is NCCL
-  point-to-point issued by the library on its own communicator, and classify + sort + pair passes + exchange
-  replay from one CUDA graph per step.  The host (this module) only builds the scene, hands the library its share
-  and launches graphs; it never waits on the device inside a step.  Cuts are re-balanced on the device every
+  point-to-point issued by the library on its own communicator, and classify + sort + pair passes + exchange are a
+  fixed launch sequence (asynchronous launches by default, one captured CUDA graph per step with
+  ``SPH_SHARD_GRAPH=1``).  The host (this module) only builds the scene, hands the library its share and launches
+  steps; it never waits on the device inside a step.  Cuts are re-balanced on the device every
   ``rebalance_every`` steps.
 
 ``tests/test_slab_gloo.py`` runs the same library code on the CPU: the host-emulated build of the kernels
@@ -392,11 +393,11 @@ def bench_main(args):
         dist.destroy_process_group()
         return 3
 
+    sampler = _bench.ClockSampler(local) if rank == 0 else None  # NVML initialised here, well before the timed region
     sim.step(max(W - P, 3))
     sim.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
-    sampler = _bench.ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     info0, launches0 = sim.info(), sim.launch_count()
@@ -496,8 +497,9 @@ def bench_main(args):
             "config": _bench.workload_config(name, sc, n_total, n_total),
             "sharding": {"slabs": slabs, "owned_total": int(tot[0].item()), "owned_max_per_rank": int(mx[0].item()),
                          "ghost_layers": GHOST_LAYERS, "halo_capacity_records": sim.halo_cap,
-                         "exchange": "one NCCL send/recv group per step issued by libsph_b200.so inside the step's CUDA "
-                                     "graph, overlapped with the interior force pass; no host synchronisation in a step; "
+                         "exchange": "one NCCL send/recv group per step issued by libsph_b200.so on its own communicator, "
+                                     "overlapped with the interior force pass; no host synchronisation in a step "
+                                     "(asynchronous launches; SPH_SHARD_GRAPH=1 replays one CUDA graph per step); "
                                      "cuts re-balanced on the device every 8 steps"},
             "parity_check": parity,
             "strong_scaling": strong,

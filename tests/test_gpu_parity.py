@@ -355,7 +355,7 @@ def test_fused_step_fields_vs_oracle_and_overflow_path():
         assert _maxrel(ps.x.to_numpy(), o.x) < 1e-6
 
 
-def _run_slab_check(nproc, extra=()):
+def _run_slab_check(nproc, extra=(), graph=False):
     import json, os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = os.path.join(root, "tools", "check_slab_parity.py")
@@ -364,7 +364,8 @@ def _run_slab_check(nproc, extra=()):
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
                "--master-addr", "127.0.0.1", "--master-port", "29533", script, *extra]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, SPH_SHARD_GRAPH="1" if graph else "0"))
     lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
     assert res.returncode == 0 and lines, res.stdout[-2000:] + res.stderr[-2000:]
     return json.loads(lines[-1])
@@ -380,8 +381,9 @@ def test_slab_two_gpus_equals_single_gpu():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
-    out = _run_slab_check(2, ["--counts", "64", "24", "24", "--steps", "60"])
-    assert out["ok"] and out["migrated"] and all(h > 0 for h in out["halo_bytes"])
+    for graph in (False, True):  # asynchronous launches (default) and CUDA-graph replay with the NCCL group captured
+        out = _run_slab_check(2, ["--counts", "64", "24", "24", "--steps", "60"], graph=graph)
+        assert out["ok"] and out["migrated"] and all(h > 0 for h in out["halo_bytes"]), (graph, out)
 
 
 def test_armadillo_bath_dynamic_full_size():

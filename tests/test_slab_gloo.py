@@ -29,10 +29,10 @@ def test_plan_slabs_balanced_and_valid():
         slab.plan_slabs(np.ones(7), 2)
 
 
-def _run(nproc, port, extra):
+def _run(nproc, port, extra, graph=False):
     import build_emu
     lib = build_emu.build()
-    env = dict(os.environ, SPH_EMU_LIB=lib, PYTHONPATH=ROOT)
+    env = dict(os.environ, SPH_EMU_LIB=lib, PYTHONPATH=ROOT, SPH_SHARD_GRAPH="1" if graph else "0")
     env.pop("SPH_B200_LIB", None)
     script = os.path.join(ROOT, "tools", "check_slab_parity.py")
     if nproc == 1:
@@ -47,8 +47,9 @@ def _run(nproc, port, extra):
 
 
 def test_sharded_two_ranks_equal_the_single_engine():
-    """Two emulated ranks over gloo: halo exchange every step, particles cross the cut (12 m/s for 16 steps)."""
-    out = _run(2, 29547, ["--counts", "24", "8", "8", "--steps", "16", "--vx", "12"])
+    """Two emulated ranks over gloo: halo exchange every step, particles cross the cut (12 m/s for 16 steps); the
+    steps replay the captured graph (SPH_SHARD_GRAPH=1: capture of the kernels AND of the transport calls)."""
+    out = _run(2, 29547, ["--counts", "24", "8", "8", "--steps", "16", "--vx", "12"], graph=True)
     assert out["ok"] and out["same_particle_set"] and out["max_dx_over_d"] < 1e-4, out
     assert out["migrated"] or out["cuts_moved"], out
     assert all(h > 0 for h in out["halo_bytes"]), out
@@ -56,7 +57,8 @@ def test_sharded_two_ranks_equal_the_single_engine():
 
 def test_three_ranks_skewed_cuts_are_rebalanced_on_the_device():
     """Deliberately skewed cuts, re-balancing every 2 steps: the cuts must move (decided on the device by both
-    ranks of a cut from the exchanged headers), particles migrate, and the result still equals the single engine."""
+    ranks of a cut from the exchanged headers), particles migrate, and the result still equals the single engine
+    (default mode: asynchronous un-graphed launches)."""
     out = _run(3, 29548, ["--counts", "32", "8", "8", "--steps", "24", "--vx", "8", "--skew", "-2", "--rebalance-every", "2"])
     assert out["ok"] and out["same_particle_set"] and out["max_dx_over_d"] < 1e-4, out
     assert out["migrated"] and out["cuts_moved"], out

@@ -39,7 +39,11 @@ torch.cuda.synchronize(); dist.barrier()
 sampler = None
 if a.sampler and rank == 0:
     import bench
-    sampler = bench.ClockSampler(int(os.environ["LOCAL_RANK"])); sampler.start()
+    sampler = bench.ClockSampler(int(os.environ["LOCAL_RANK"]))
+sim.step(5)
+torch.cuda.synchronize(); dist.barrier()
+if sampler:
+    sampler.start()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); sim.step(a.steps); e1.record(); torch.cuda.synchronize()
 if sampler:
