@@ -27,9 +27,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# the CPU arm: pin the OpenMP threads (must be set before libgomp initialises); the thread COUNT is chosen below
-os.environ.setdefault("OMP_PROC_BIND", "close")
-os.environ.setdefault("OMP_PLACES", "cores")
+
+
+def pin_openmp_for_the_cpu_arm():
+    """The CPU arm pins its OpenMP threads (must happen before libgomp initialises, i.e. before torch or the oracle are
+    imported); the thread COUNT is chosen in best_thread_count.  NEVER in a multi-rank run: with OMP_NUM_THREADS=1
+    (torchrun's default) the binding pins the main thread of EVERY rank to the first place -- all ranks time-slice one
+    core and the asynchronous launches of a sharded step crawl (1.44 instead of 0.45 ms per step at 4 GPUs)."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
 
 METRIC = "M particle-updates/sec (SPH steps/sec x particles)"
 UNIT = "M particle-updates/s"
@@ -140,16 +146,20 @@ class ClockSampler:
             pynvml, h = self.nvml
 
             def poll():
+                mode = os.environ.get("SPH_BENCH_SAMPLER", "both")  # experiments: "clock", "reasons", "both"
+                period = float(os.environ.get("SPH_BENCH_SAMPLER_PERIOD_S", "0.010"))
                 while not self._stop.is_set():
                     try:
-                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                        r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
-                        for name, bit in self.BITS.items():
-                            if r & bit:
-                                self.reasons.add(name)
+                        if mode != "reasons":
+                            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        if mode != "clock":
+                            r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                            for name, bit in self.BITS.items():
+                                if r & bit:
+                                    self.reasons.add(name)
                     except Exception:
                         pass
-                    self._stop.wait(0.010)
+                    self._stop.wait(period)
 
             self.thread = threading.Thread(target=poll, daemon=True)
             self.thread.start()
@@ -501,7 +511,11 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
+        if int(os.environ.get("RANK", 0)) == 0:
+            pin_openmp_for_the_cpu_arm()
         return run_reference(args)
+    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        pin_openmp_for_the_cpu_arm()  # the cpu_baseline leg of the single-GPU line
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         from sph_taichi_b200 import slab
         return slab.bench_main(args)

@@ -335,12 +335,14 @@ int launch_boundary_volume(SphCtx *c, int moving, cudaStream_t st, int64_t *kern
 }
 
 int launch_rigid_solve(SphCtx *c, cudaStream_t st, int64_t *kernels) {
-    // sph_base.py:247-260: per dynamic body solve_constraints, then enforce_boundary_3D(solid)
-    for (size_t b = 0; b < c->bodies.size(); ++b) {
-        k_rigid<<<1, RIGID_THREADS, 0, st>>>(c->P, c->S, dev_bodies(c), (int)b, 2, nullptr);
-        k_enforce_boundary_solid<<<blocks_for(c->P.n_solid, 256), 256, 0, st>>>(c->P, c->S);
-        *kernels += 2;
-    }
+    // sph_base.py:247-260: per dynamic body solve_constraints, then enforce_boundary_3D(solid) -- all bodies in ONE
+    // launch (one CTA per body carries the clamps of the whole loop for its own particles, see k_rigid), the dynamic
+    // solids outside every body in a second one
+    const int nb = (int)c->bodies.size();
+    if (nb == 0) return SPH_OK;
+    k_rigid<<<nb, RIGID_THREADS, 0, st>>>(c->P, c->S, dev_bodies(c), 0, 2, nullptr, nb);
+    k_enforce_boundary_solid<<<blocks_for(c->P.n_solid, 256), 256, 0, st>>>(c->P, c->S, nb, dev_bodies(c), nb);
+    *kernels += 2;
     CUDA_TRY(c, cudaGetLastError());
     return SPH_OK;
 }
@@ -617,7 +619,7 @@ int sph_set_rigid_bodies(SphCtx *ctx, const SphRigidBody *bodies, int32_t n_bodi
 static int rigid_call(SphCtx *ctx, int32_t body, int mode, float *out, void *stream) {
     if (!ctx) return SPH_E_ARG;
     if (body < 0 || body >= (int)ctx->bodies.size()) return fail(ctx, SPH_E_ARG, "rigid body index out of range");
-    k_rigid<<<1, RIGID_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S, dev_bodies(ctx), body, mode, out);
+    k_rigid<<<1, RIGID_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(ctx->P, ctx->S, dev_bodies(ctx), body, mode, out, 0);
     ctx->launches += 1;
     if (mode == 2) { ctx->built = false; ctx->list_valid = false; }  // modes 0 / 1 only read
     CUDA_TRY(ctx, cudaGetLastError());

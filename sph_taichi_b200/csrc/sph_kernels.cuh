@@ -568,15 +568,26 @@ __global__ void k_enforce_boundary(DevParams P, DevArrays S, int particle_type) 
     S.veld[i] = v;
 }
 
-// enforce_boundary_3D(material_solid) restricted to the solid list (cheaper than a full sweep)
-__global__ void k_enforce_boundary_solid(DevParams P, DevArrays S) {
+struct RigidBodyDev {
+    int32_t object_id, solid_begin, solid_end;
+    float rest_cm[3];
+    float R[9];   // rotation of the last solve_constraints
+    float cm[3];  // centre of mass of the last solve_constraints
+};
+
+// enforce_boundary_3D(material_solid) restricted to the solid list (cheaper than a full sweep).  reps > 1 with
+// skip_bodies: the fused step applies the n clamps of the reference's body loop to the dynamic solids that belong to NO
+// shape-matched body here (k_rigid does it for the bodies' own particles).
+__global__ void k_enforce_boundary_solid(DevParams P, DevArrays S, int reps, const RigidBodyDev *skip_bodies, int n_skip) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= P.n_solid) return;
+    for (int b = 0; b < n_skip; ++b)
+        if (s >= skip_bodies[b].solid_begin && s < skip_bodies[b].solid_end) return;
     int i = S.solid_slot[s];
     uint32_t fl = __float_as_uint(S.misc[i].z);
     if (!(fl & FLAG_DYNAMIC)) return;
     float4 p = S.posm[i], v = S.veld[i];
-    wall_clamp(P, p, v);
+    for (int r = 0; r < reps; ++r) wall_clamp(P, p, v);
     S.posm[i] = p;
     S.veld[i] = v;
 }
@@ -586,13 +597,6 @@ __global__ void k_enforce_boundary_solid(DevParams P, DevArrays S) {
 // reductions (deterministic), polar decomposition in fp64 on one thread.
 // =====================================================================================
 constexpr int RIGID_THREADS = 1024;
-
-struct RigidBodyDev {
-    int32_t object_id, solid_begin, solid_end;
-    float rest_cm[3];
-    float R[9];   // rotation of the last solve_constraints
-    float cm[3];  // centre of mass of the last solve_constraints
-};
 
 template <int NV>
 __device__ __forceinline__ void block_reduce(float (&v)[NV], float *smem /* [32 * NV] */) {
@@ -689,10 +693,17 @@ __device__ void polar_rotation_f64(const double A[9], double R[9], bool &ok) {
 // mode 0: compute_com -> out[3];  mode 1: store rest cm;  mode 2: solve_constraints.
 // One gather pass accumulates the raw moments  M = sum m,  X = sum m x,  Q = sum m q,  XQ = sum m x (x) q
 // (q = x_0 - rest_cm); then  cm = X / M  and  A = sum m (x - cm) (x) q = XQ - cm (x) Q  (sph_base.py:182-211).
+// n_step_bodies > 0 (fused step, mode 2, one CTA per body = blockIdx.x): the reference solves the bodies one after
+// the other and clamps ALL dynamic solid particles to the walls after each solve (sph_base.py:247-260), i.e. a
+// particle of body b is clamped b times before its body is solved and n - b times after.  The bodies' particle
+// sets are disjoint and a clamp only looks at the particle itself, so the same sequence runs here per body in ONE
+// launch (3 bodies: 6 launches -> 2, bit-identical).
 __global__ void __launch_bounds__(RIGID_THREADS) k_rigid(DevParams P, DevArrays S, RigidBodyDev *bodies, int body,
-                                                          int mode, float *out) {
+                                                          int mode, float *out, int n_step_bodies) {
     __shared__ float red[32 * 16];
     __shared__ float s_R[9];
+    if (n_step_bodies > 0) body = blockIdx.x;
+    const int pre_clamps = n_step_bodies > 0 ? body : 0, post_clamps = n_step_bodies > 0 ? n_step_bodies - body : 0;
     RigidBodyDev *B = bodies + body;
     const int b0 = B->solid_begin, b1 = B->solid_end;
     const float r0 = B->rest_cm[0], r1 = B->rest_cm[1], r2 = B->rest_cm[2];
@@ -704,6 +715,12 @@ __global__ void __launch_bounds__(RIGID_THREADS) k_rigid(DevParams P, DevArrays 
         uint32_t fl = __float_as_uint(S.misc[i].z);
         if (!(fl & FLAG_DYNAMIC)) continue;  // compute_com counts dynamic rigid particles only (Q8)
         float4 p = S.posm[i], x0 = S.x0id[i];
+        if (pre_clamps > 0) {  // the clamps the earlier bodies' iterations applied to this particle
+            float4 v = S.veld[i];
+            for (int r = 0; r < pre_clamps; ++r) wall_clamp(P, p, v);
+            S.posm[i] = p;
+            S.veld[i] = v;
+        }
         float mass = P.m_V0 * S.veld[i].w;
         float q[3] = {x0.x - r0, x0.y - r1, x0.z - r2};
         float x[3] = {p.x, p.y, p.z};
@@ -752,6 +769,11 @@ __global__ void __launch_bounds__(RIGID_THREADS) k_rigid(DevParams P, DevArrays 
         float gy = cmy + (s_R[3] * q0 + s_R[4] * q1 + s_R[5] * q2);
         float gz = cmz + (s_R[6] * q0 + s_R[7] * q1 + s_R[8] * q2);
         p.x += (gx - p.x) * 1.0f; p.y += (gy - p.y) * 1.0f; p.z += (gz - p.z) * 1.0f;
+        if (post_clamps > 0) {  // this body's own clamp and those of the later bodies' iterations
+            float4 v = S.veld[i];
+            for (int r = 0; r < post_clamps; ++r) wall_clamp(P, p, v);
+            S.veld[i] = v;
+        }
         S.posm[i] = p;
     }
 }
