@@ -297,19 +297,23 @@ int launch_neighbor_build(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *k
 
 // density + neighbour lists, then forces (+ integration).  SPH_DENSITY_VARIANT / SPH_FORCE_VARIANT = 0
 // select the ablation variants (second dense loop for the density sum; separate advect kernel).
-void launch_pair_density(SphCtx *c, cudaStream_t st, int64_t *kernels) {
+void launch_pair_density(SphCtx *c, cudaStream_t st, int64_t *kernels, int split_mode = 0) {
     const DevParams &P = c->P;
     const int blocks = blocks_for(P.n, DENS_WARPS * 32);
-    if (c->var_density == 0) PDL_LAUNCH((k_density_tma<false, false>), blocks, DENS_WARPS * 32, st, P, c->S);
-    else if (P.dfsph || c->var_density == 2) PDL_LAUNCH((k_density_tma<true, false>), blocks, DENS_WARPS * 32, st, P, c->S);
-    else PDL_LAUNCH((k_density_tma<true, true>), blocks, DENS_WARPS * 32, st, P, c->S);
+    if (c->var_density == 0) PDL_LAUNCH((k_density_tma<false, false>), blocks, DENS_WARPS * 32, st, P, c->S, split_mode);
+    else if (P.dfsph || c->var_density == 2) PDL_LAUNCH((k_density_tma<true, false>), blocks, DENS_WARPS * 32, st, P, c->S, split_mode);
+    else PDL_LAUNCH((k_density_tma<true, true>), blocks, DENS_WARPS * 32, st, P, c->S, split_mode);
     *kernels += 1;
 }
 void launch_pair_force_and_advect(SphCtx *c, cudaStream_t st, StageTimer *tm, int64_t *kernels, int split_mode = 0) {
     const DevParams &P = c->P;
     if (P.uniform_fluid && c->var_force != 0) {
-        PDL_LAUNCH((k_force_packed<FORCE_BATCH, FORCE_THREADS, true>), blocks_for(P.n, FORCE_THREADS), FORCE_THREADS, st, P, c->S,
-                   split_mode);
+        if (P.slab_on)
+            PDL_LAUNCH((k_force_packed<FORCE_BATCH, FORCE_THREADS, true, true>), blocks_for(P.n, FORCE_THREADS), FORCE_THREADS, st, P,
+                       c->S, split_mode);
+        else
+            PDL_LAUNCH((k_force_packed<FORCE_BATCH, FORCE_THREADS, true>), blocks_for(P.n, FORCE_THREADS), FORCE_THREADS, st, P, c->S,
+                       split_mode);
         *kernels += 1;
         if (tm) tm->mark(T_ADVECT);
         if (c->has_dynamic_solids && P.n_solid > 0) {
@@ -761,7 +765,8 @@ int shard_exchange(SphCtx *c, cudaStream_t st, bool wide) {
     return SPH_OK;
 }
 
-// plan -> classify + sort -> info -> [density -> boundary forces] -> pack -> { exchange || interior forces }
+// plan -> classify + sort -> info -> boundary densities -> boundary forces (-> staging) ->
+// { exchange || interior densities -> apply -> interior forces }
 // ev[7] (optional): CUDA events at the stage boundaries, [5..6] around the exchange (sph_shard_profile_step)
 // wide: this sequence's exchange feeds a re-balancing step and carries sgw + 2 layers instead of sgw + 1
 int shard_sequence(SphCtx *c, cudaStream_t st, bool compute, bool wide, int64_t *kernels, cudaEvent_t *ev = nullptr) {
@@ -773,18 +778,21 @@ int shard_sequence(SphCtx *c, cudaStream_t st, bool compute, bool wide, int64_t 
     k_shard_info<<<1, 32, 0, st>>>(c->P, c->S, c->P.sgw + (wide ? 2 : 1), wide ? c->P.halo_cap : c->narrow_cap);
     *kernels += 1;
     if (ev) cudaEventRecord(ev[1], st);
+    const dim3 pack_grid(blocks_for(c->P.halo_cap, 256), 2);
     if (compute) {
-        launch_pair_density(c, st, kernels);
+        // boundary first: densities within one layer of the send ranges, then forces + integration of the send ranges
+        // -- written into the send staging, not into the arrays: the interior densities still read these positions
+        launch_pair_density(c, st, kernels, /*split_mode=*/1);
         if (ev) cudaEventRecord(ev[2], st);
-        launch_pair_force_and_advect(c, st, nullptr, kernels, /*split_mode=*/1);  // the particles about to be sent
-    } else if (ev) {
-        cudaEventRecord(ev[2], st);
+        launch_pair_force_and_advect(c, st, nullptr, kernels, /*split_mode=*/1);
+    } else {
+        if (ev) cudaEventRecord(ev[2], st);
+        k_shard_apply<<<pack_grid, 256, 0, st>>>(c->P, c->S, /*copy_all=*/1);  // first exchange: the unchanged records
+        *kernels += 1;
     }
-    k_shard_pack<<<dim3(blocks_for(c->P.halo_cap, 256), 2), 256, 0, st>>>(c->P, c->S);
-    *kernels += 1;
     CUDA_TRY(c, cudaGetLastError());
     if (ev) cudaEventRecord(ev[3], st);
-    // the exchange for the NEXT step runs on the communication stream while the interior is still computed
+    // the exchange for the NEXT step runs on the communication stream while the interior is computed
 #ifdef SPH_EMU
     cudaStream_t cs = st;  // the emulated runtime is synchronous
 #else
@@ -796,7 +804,12 @@ int shard_sequence(SphCtx *c, cudaStream_t st, bool compute, bool wide, int64_t 
     rc = shard_exchange(c, cs, wide);
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[6], cs);
-    if (compute) launch_pair_force_and_advect(c, st, nullptr, kernels, /*split_mode=*/2);
+    if (compute) {
+        launch_pair_density(c, st, kernels, /*split_mode=*/2);
+        k_shard_apply<<<pack_grid, 256, 0, st>>>(c->P, c->S, /*copy_all=*/0);  // boundary particles take their new state
+        *kernels += 1;
+        launch_pair_force_and_advect(c, st, nullptr, kernels, /*split_mode=*/2);
+    }
 #ifndef SPH_EMU
     CUDA_TRY(c, cudaEventRecord(c->ev_exchanged, cs));
     CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_exchanged, 0));

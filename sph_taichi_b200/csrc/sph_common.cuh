@@ -109,6 +109,7 @@ enum {
     SD_HDR_L = 16, SD_HDR_R = 32,                // headers received from the left / right neighbour
     SD_SENT_LO = 48, SD_SENT_HI,                 // records sent so far (64-bit, for the halo statistics)
     SD_DENS1 = 50,
+    SD_DB_L1 = 51, SD_DB_R0 = 52,                // boundary density ranges: [DENS0, DB_L1) and [DB_R0, DENS1)
     SD_INTS = 64
 };
 constexpr int SHARD_MIN_WIDTH = 5;  // a slab gives a layer away only while it is wider than this (ghost band 2 + send range 4 must fit)

@@ -183,7 +183,14 @@ __global__ void k_shard_info(DevParams P, DevArrays S, int send_layers, int send
     sd[SD_SEND_L0] = l0; sd[SD_SEND_L1] = l1; sd[SD_SEND_R0] = r0; sd[SD_SEND_R1] = r1;
     // densities are needed for the owned particles and the FIRST ghost layer of each side (the second one only
     // serves as neighbours of the first): one contiguous index range
-    sd[SD_DENS0] = start_of_layer(sx0 - 1); sd[SD_DENS1] = start_of_layer(sx1 + 1);
+    const int d0 = start_of_layer(sx0 - 1), d1 = start_of_layer(sx1 + 1);
+    sd[SD_DENS0] = d0; sd[SD_DENS1] = d1;
+    // ... and FIRST for everything within one layer of the send ranges (the boundary forces need exactly those), so
+    // that the exchange can start before the interior densities: [d0, db_l1) and [db_r0, d1)
+    int db_l1 = P.has_left ? start_of_layer(min(sx0 + send_layers + 1, sx1 + 1)) : d0;
+    int db_r0 = P.has_right ? start_of_layer(max(sx1 - send_layers - 1, sx0 - 1)) : d1;
+    db_r0 = max(db_r0, db_l1);
+    sd[SD_DB_L1] = db_l1; sd[SD_DB_R0] = db_r0;
     sd[SD_FLAGS] = (int32_t)(*S.status);
     unsigned long long sent = ((unsigned long long)(uint32_t)sd[SD_SENT_HI] << 32) | (uint32_t)sd[SD_SENT_LO];
     sent += (unsigned long long)(l1 - l0) + (unsigned long long)(r1 - r0);
@@ -195,9 +202,10 @@ __global__ void k_shard_info(DevParams P, DevArrays S, int send_layers, int send
     }
 }
 
-// Pack the (already advanced) boundary particles into the send staging: slot s of side 0 is record l0 + s, of
-// side 1 record r0 + s.  acc is not exchanged (recomputed every step).
-__global__ void k_shard_pack(DevParams P, DevArrays S) {
+// The boundary pass of the force kernel wrote the advanced state of the send ranges into the staging (side, slot) =
+// (0, i - l0) / (1, i - r0); after the interior densities are done it goes back into the packed arrays.
+// copy_all = 1 (first exchange, no physics yet): pack the unchanged records instead.
+__global__ void k_shard_apply(DevParams P, DevArrays S, int copy_all) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int side = blockIdx.y;
     const int32_t *sd = S.sd;
@@ -206,10 +214,15 @@ __global__ void k_shard_pack(DevParams P, DevArrays S) {
     if (s >= e - b) return;
     const int i = b + s;
     SPH_EMU_CHECK(s < P.halo_cap && i >= 0 && i < P.n);
-    S.stage[side][0][s] = S.posm[i];
-    S.stage[side][1][s] = S.veld[i];
-    S.stage[side][2][s] = S.x0id[i];
-    S.stage[side][3][s] = S.misc[i];
+    if (copy_all) {
+        S.stage[side][0][s] = S.posm[i];
+        S.stage[side][1][s] = S.veld[i];
+        S.stage[side][2][s] = S.x0id[i];
+        S.stage[side][3][s] = S.misc[i];
+    } else {
+        S.posm[i] = S.stage[side][0][s];  // (a particle inside both send ranges holds the same values in both stagings)
+        S.veld[i] = S.stage[side][1][s];
+    }
 }
 
 // In-place inclusive prefix sum over the per-cell counts (the reference's
@@ -871,8 +884,10 @@ __device__ __forceinline__ uint32_t scan_chunk(const DevParams &P, const float4 
 #endif
 // FASTW (with INLINE_W): the branch-free spline_w_norm() with the 2k factor applied once per particle;
 // DFSPH keeps the reference's piecewise form (its solver loops count iterations against the oracle).
+// split_mode (sharded steps): 1 = only the particles within one layer of the send ranges, 2 = only the others,
+// 0 = all that need a density.
 template <bool INLINE_W, bool FASTW>
-__global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tma(DevParams P, DevArrays S) {
+__global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tma(DevParams P, DevArrays S, int split_mode) {
     pdl_wait();
     __shared__ __align__(128) float4 s_win[DENS_WARPS][2][WIN_CAP + 32];
     __shared__ __align__(8) uint64_t s_bar[DENS_WARPS][2];
@@ -884,8 +899,19 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
 
     // one tile = blockDim.x consecutive particles starting at i - threadIdx.x; i_end bounds the particles that need
     // a density
-    auto tile = [&](const int i, const int i_begin, const int i_end) {
-    bool live = i >= i_begin && i < i_end;
+    auto tile = [&](const int i) {
+    bool live = i < P.n;
+    if (P.slab_on) {
+        // sharded steps: the grid covers the capacity (the hardware block scheduler balances better than a persistent
+        // tile loop: 0.385 vs 0.49 ms at 2 M particles per rank, profiles/r02_shard_timing.txt); only owned particles
+        // + the first ghost layer per side -- one index range of the device-resident step state -- need a density
+        const int32_t *sd = S.sd;
+        live = i >= sd[SD_DENS0] && i < sd[SD_DENS1];
+        if (split_mode) {
+            const bool boundary = i < sd[SD_DB_L1] || i >= sd[SD_DB_R0];
+            live = live && ((split_mode == 1) == boundary);
+        }
+    }
     float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), mi = pi;
     uint32_t fl = 0;
     if (live) { pi = S.posm[i]; mi = S.misc[i]; fl = __float_as_uint(mi.z); }
@@ -1048,10 +1074,7 @@ __global__ void __launch_bounds__(DENS_WARPS * 32, DENS_MIN_BLOCKS) k_density_tm
         S.fpv[2 * (size_t)i + 1] = make_float4(vb.x, vb.y, vb.z, dp);
     }
     };  // tile
-    // sharded steps: the grid covers the capacity (the hardware block scheduler balances better than a persistent
-    // tile loop: 0.385 vs 0.49 ms at 2 M particles per rank, profiles/r02_shard_timing.txt); only owned particles
-    // + the first ghost layer per side -- one index range of the device-resident step state -- need a density
-    tile(blockIdx.x * blockDim.x + threadIdx.x, P.slab_on ? S.sd[SD_DENS0] : 0, P.slab_on ? S.sd[SD_DENS1] : P.n);
+    tile(blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // Fused force pass, general particle masses: 3 x 16 B gathered per neighbour.
@@ -1156,7 +1179,9 @@ __device__ __forceinline__ void force_pair_packed(const DevParams &P, const DevA
 // (k_shard_info), 2 = only the others, 0 = all -- the halo exchange of the NEXT step starts as soon as the
 // boundary particles are final and overlaps the interior.
 static_assert(LIST_PAD % FORCE_BATCH == 0 && NBR_CAP % LIST_PAD == 0, "list padding must cover a force batch");
-template <int B, int THREADS, bool FUSE_ADVECT>
+// SHARD: the sharded steps' instantiation (send-range split, staging of the boundary particles); compile-time so
+// that the single-GPU kernel keeps its register budget.
+template <int B, int THREADS, bool FUSE_ADVECT, bool SHARD = false>
 __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevParams P, DevArrays S,
                                                                             int split_mode) {
     pdl_wait();
@@ -1214,19 +1239,38 @@ __global__ void __launch_bounds__(THREADS, FORCE_MIN_BLOCKS) k_force_packed(DevP
     }
     float4 a = make_float4(A.npx + A.prx, A.npy + A.pry, A.npz + A.prz, 0.f);
     S.acc[i] = a;
-    if (FUSE_ADVECT && (fl & FLAG_DYNAMIC)) {
+    if (FUSE_ADVECT) {
         float4 p = make_float4(pi.x, pi.y, pi.z, P.fluid_mV);
         float4 v = make_float4(vi.x, vi.y, vi.z, S.veld[i].w);
-        v.x += P.dt * a.x; v.y += P.dt * a.y; v.z += P.dt * a.z;
-        p.x += P.dt * v.x; p.y += P.dt * v.y; p.z += P.dt * v.z;
-        wall_clamp(P, p, v);
-        S.posm[i] = p;
-        S.veld[i] = v;
+        if (fl & FLAG_DYNAMIC) {
+            v.x += P.dt * a.x; v.y += P.dt * a.y; v.z += P.dt * a.z;
+            p.x += P.dt * v.x; p.y += P.dt * v.y; p.z += P.dt * v.z;
+            wall_clamp(P, p, v);
+        }
+        if (SHARD && split_mode == 1) {
+            // sharded boundary pass: the interior DENSITIES are still to come and read the positions of these
+            // particles, so the advanced state goes to the send staging only (this IS the pack step; the halo
+            // exchange starts right after this kernel) and k_shard_apply copies it back later
+            const int32_t *sd = S.sd;
+            const float4 xo = S.x0id[i];
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const int b0 = side == 0 ? sd[SD_SEND_L0] : sd[SD_SEND_R0], b1 = side == 0 ? sd[SD_SEND_L1] : sd[SD_SEND_R1];
+                if (i >= b0 && i < b1) {
+                    const int slot = i - b0;
+                    SPH_EMU_CHECK(slot < P.halo_cap);
+                    S.stage[side][0][slot] = p; S.stage[side][1][slot] = v; S.stage[side][2][slot] = xo; S.stage[side][3][slot] = mi;
+                }
+            }
+        } else if (fl & FLAG_DYNAMIC) {
+            S.posm[i] = p;
+            S.veld[i] = v;
+        }
     }
     };  // one particle
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
-    if (P.slab_on) {  // sharded: owned particles only, split into the send ranges and the rest
+    if (SHARD) {  // owned particles only, split into the send ranges and the rest
         const int32_t *sd = S.sd;
         if (i < sd[SD_OWN0] || i >= sd[SD_OWN1]) return;
         const bool boundary = (i >= sd[SD_SEND_L0] && i < sd[SD_SEND_L1]) || (i >= sd[SD_SEND_R0] && i < sd[SD_SEND_R1]);
