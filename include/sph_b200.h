@@ -170,9 +170,10 @@ int sph_dfsph_op(SphCtx *ctx, int32_t op, float arg, void *out_dev, void *stream
  * Everything a step needs lives on the device -- live count, slab bounds, send / receive ranges, record counts
  * (carried in-band in a header) -- so a whole sharded step is a fixed launch sequence (capturable as ONE CUDA graph):
  *
- *     plan (receive counts, cut re-balancing) -> classify + sort -> info (send ranges) -> density ->
- *     forces + integration of the boundary particles -> pack -> { halo exchange of the NEXT step  ||
- *     forces + integration of the interior }
+ *     plan (receive counts, cut re-balancing) -> classify + sort -> info (send ranges) -> densities within one
+ *     layer of the send ranges -> forces + integration of the send ranges, written straight into the send staging
+ *     -> { halo exchange of the NEXT step  ||  interior densities -> staged state back into the arrays -> interior
+ *     forces + integration }
  *
  * and the host only launches.  Every record is classified as owned / ghost / dropped from its position
  * alone (both ranks evaluate the same fp32 expression), so migration needs no extra message; cuts move by at
@@ -208,10 +209,10 @@ int sph_halo_exchange(SphCtx *ctx, void *stream);
  * own_end, sendL_begin, sendL_end, sendR_begin, sendR_end, recv_left, recv_right, n_sorted, status,
  * 0}; out_sent (may be NULL) = halo records sent so far */
 int sph_shard_info(SphCtx *ctx, int32_t *out16, uint64_t *out_sent, void *stream);
-/* ONE un-graphed sharded step with CUDA events between its stages; ms_out5 = {sort + bookkeeping, density,
- * boundary forces + pack, max(interior forces, halo exchange), the exchange alone on the communication stream};
- * synchronises */
-int sph_shard_profile_step(SphCtx *ctx, float *ms_out5, void *stream);
+/* ONE un-graphed sharded step with CUDA events between its stages; ms_out6 = {plan + sort + info, boundary
+ * densities, boundary forces (-> staging), interior densities, apply + interior forces (+ waiting for the exchange,
+ * if it is not hidden), the exchange alone on the communication stream}; synchronises */
+int sph_shard_profile_step(SphCtx *ctx, float *ms_out6, void *stream);
 int sph_state_offsets(SphCtx *ctx, uint64_t *out5); /* byte offsets of posm, veld, x0id, misc, acc in the workspace */
 
 /* ---- diagnostics ----------------------------------------------------------------------------- */

@@ -148,6 +148,10 @@ struct SphCtx {
     cudaGraphExec_t graph_shard[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [parity][wide exchange]
     int64_t graph_shard_kernels[2][2] = {{0, 0}, {0, 0}};
     int32_t narrow_cap = 0;      // records per side of the usual (sgw + 1 layers) exchange; halo_cap = sgw + 2 layers
+    // hide the exchange behind the interior densities too (boundary densities first): pays off when a rank talks to
+    // two neighbours and the exchange outlasts the interior force pass (8 ranks: 0.38 vs 0.2 ms); with one neighbour
+    // or short exchanges the second density launch costs more than it hides (4 ranks: 0.457 vs 0.444 ms per step)
+    bool split_density = false;
     int64_t shard_sequences = 0;  // sequences run so far (begin = 0): sequence q feeds the plan kernel of q + 1
 };
 
@@ -767,7 +771,8 @@ int shard_exchange(SphCtx *c, cudaStream_t st, bool wide) {
 
 // plan -> classify + sort -> info -> boundary densities -> boundary forces (-> staging) ->
 // { exchange || interior densities -> apply -> interior forces }
-// ev[7] (optional): CUDA events at the stage boundaries, [5..6] around the exchange (sph_shard_profile_step)
+// ev[8] (optional): CUDA events at the stage boundaries, [5..6] around the exchange, [7] after the interior
+// densities (sph_shard_profile_step)
 // wide: this sequence's exchange feeds a re-balancing step and carries sgw + 2 layers instead of sgw + 1
 int shard_sequence(SphCtx *c, cudaStream_t st, bool compute, bool wide, int64_t *kernels, cudaEvent_t *ev = nullptr) {
     if (ev) cudaEventRecord(ev[0], st);
@@ -780,9 +785,10 @@ int shard_sequence(SphCtx *c, cudaStream_t st, bool compute, bool wide, int64_t 
     if (ev) cudaEventRecord(ev[1], st);
     const dim3 pack_grid(blocks_for(c->P.halo_cap, 256), 2);
     if (compute) {
-        // boundary first: densities within one layer of the send ranges, then forces + integration of the send ranges
-        // -- written into the send staging, not into the arrays: the interior densities still read these positions
-        launch_pair_density(c, st, kernels, /*split_mode=*/1);
+        // boundary first: densities within one layer of the send ranges (split_density; otherwise all densities),
+        // then forces + integration of the send ranges -- written into the send staging, not into the arrays: the
+        // interior densities still read these positions
+        launch_pair_density(c, st, kernels, /*split_mode=*/c->split_density ? 1 : 0);
         if (ev) cudaEventRecord(ev[2], st);
         launch_pair_force_and_advect(c, st, nullptr, kernels, /*split_mode=*/1);
     } else {
@@ -805,7 +811,8 @@ int shard_sequence(SphCtx *c, cudaStream_t st, bool compute, bool wide, int64_t 
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[6], cs);
     if (compute) {
-        launch_pair_density(c, st, kernels, /*split_mode=*/2);
+        if (c->split_density) launch_pair_density(c, st, kernels, /*split_mode=*/2);
+        if (ev) cudaEventRecord(ev[7], st);
         k_shard_apply<<<pack_grid, 256, 0, st>>>(c->P, c->S, /*copy_all=*/0);  // boundary particles take their new state
         *kernels += 1;
         launch_pair_force_and_advect(c, st, nullptr, kernels, /*split_mode=*/2);
@@ -914,6 +921,8 @@ int sph_shard_configure(SphCtx *ctx, int32_t x_lo, int32_t x_hi, int32_t ghost_l
     ctx->P.rebalance_every = rebalance_every;
     ctx->narrow_cap = (int32_t)((halo_capacity * (ghost_layers + 1) + ghost_layers + 1) / (ghost_layers + 2));
     ctx->shard_sequences = 0;
+    ctx->split_density = ctx->world > 4;
+    if (const char *v = std::getenv("SPH_SHARD_SPLIT_DENSITY")) ctx->split_density = std::atoi(v) != 0;
     ctx->P.n = (int32_t)ctx->n_max;  // from here on n is the CAPACITY; the live count is device state
     ctx->shard_begun = false;
     bind_arrays(ctx);
@@ -1002,21 +1011,25 @@ int sph_shard_info(SphCtx *ctx, int32_t *out16, uint64_t *out_sent, void *stream
     return SPH_OK;
 }
 
-int sph_shard_profile_step(SphCtx *ctx, float *ms_out5, void *stream) {
+int sph_shard_profile_step(SphCtx *ctx, float *ms_out6, void *stream) {
     REQUIRE_SHARD(ctx);
-    if (!ms_out5) return SPH_E_ARG;
+    if (!ms_out6) return SPH_E_ARG;
     if (!ctx->shard_begun) return fail(ctx, SPH_E_ARG, "sph_shard_begin was not called");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaEvent_t ev[7];
-    for (int k = 0; k < 7; ++k) CUDA_TRY(ctx, cudaEventCreate(&ev[k]));
+    cudaEvent_t ev[8];
+    for (int k = 0; k < 8; ++k) CUDA_TRY(ctx, cudaEventCreate(&ev[k]));
     int rc = shard_sequence(ctx, st, /*compute=*/true, shard_wide(ctx), &ctx->launches, ev);
     if (rc) return rc;
     ctx->shard_sequences += 1;
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms_out5[k], ev[k], ev[k + 1]);
-    ms_out5[4] = 0.f;
-    if (ctx->world > 1) cudaEventElapsedTime(&ms_out5[4], ev[5], ev[6]);
-    for (int k = 0; k < 7; ++k) cudaEventDestroy(ev[k]);
+    cudaEventElapsedTime(&ms_out6[0], ev[0], ev[1]);  // plan + sort + info
+    cudaEventElapsedTime(&ms_out6[1], ev[1], ev[2]);  // boundary densities
+    cudaEventElapsedTime(&ms_out6[2], ev[2], ev[3]);  // boundary forces (-> staging)
+    cudaEventElapsedTime(&ms_out6[3], ev[3], ev[7]);  // interior densities
+    cudaEventElapsedTime(&ms_out6[4], ev[7], ev[4]);  // apply + interior forces + waiting for the exchange, if any
+    ms_out6[5] = 0.f;
+    if (ctx->world > 1) cudaEventElapsedTime(&ms_out6[5], ev[5], ev[6]);
+    for (int k = 0; k < 8; ++k) cudaEventDestroy(ev[k]);
     return SPH_OK;
 }
 

@@ -186,11 +186,11 @@ class ShardedSimulation:
     def profile_step(self):
         """ONE un-graphed step with CUDA events between the stages (synchronises)."""
         e = self.eng
-        buf = (C.c_float * 5)()
+        buf = (C.c_float * 6)()
         e._check(e.lib.sph_shard_profile_step(e.ctx, buf, e._stream()), "sph_shard_profile_step")
         self.steps_done += 1
-        return {"sort_ms": buf[0], "density_ms": buf[1], "boundary_force_pack_ms": buf[2],
-                "interior_force_or_exchange_ms": buf[3], "exchange_ms": buf[4]}
+        return {"sort_ms": buf[0], "density_boundary_ms": buf[1], "force_boundary_ms": buf[2], "density_interior_ms": buf[3],
+                "force_interior_ms": buf[4], "exchange_ms": buf[5]}
 
     def info(self):
         """The device-resident step state (synchronising read); raises on a capacity / out-of-grid flag."""
@@ -430,8 +430,9 @@ def bench_main(args):
             acc[k_] = acc.get(k_, 0.0) + v_ / R
     live_now = sim.info()
     peak, peak_src = _bench.measured_hbm_peak()
-    roof = torch.tensor([acc["density_ms"], acc["boundary_force_pack_ms"] + acc["interior_force_or_exchange_ms"],
-                         float(live_now["n_live"]), float(live_now["owned"]), acc["sort_ms"]], device=dev, dtype=torch.float64)
+    roof = torch.tensor([acc["density_boundary_ms"] + acc["density_interior_ms"], acc["force_boundary_ms"] + acc["force_interior_ms"],
+                         float(live_now["n_live"]), float(live_now["owned"]), acc["sort_ms"], acc["exchange_ms"]],
+                        device=dev, dtype=torch.float64)
     roof_max = roof.clone()
     dist.all_reduce(roof_max, op=dist.ReduceOp.MAX)
 
@@ -486,10 +487,12 @@ def bench_main(args):
         kernels.sort(key=lambda e_: -e_["avg_launch_ms"])
         roofline = dict(kernels[0])
         roofline.update(peak_source=peak_src, kernels=kernels, sort_ms_slowest_rank=float(roof_max[4].item()),
+                        exchange_ms_slowest_rank=float(roof_max[5].item()),
                         note="per GPU, slowest rank; CUDA events between the stages of un-graphed sharded steps (10 steps); "
-                             "density runs over owned + ghost particles, forces over owned; the force figure includes the "
-                             "boundary pass, the pack kernel and max(interior pass, halo exchange); the pair kernels are "
-                             "fp32-issue / LSU bound, not HBM bound (DESIGN.md section 5)")
+                             "density = boundary + interior launches over owned + first-ghost-layer particles, forces = boundary "
+                             "+ interior launches over owned particles (the interior figure includes waiting for the halo "
+                             "exchange if it is not hidden behind the interior passes); the pair kernels are fp32-issue / LSU "
+                             "bound, not HBM bound (DESIGN.md section 5)")
         line = {
             "metric": _bench.METRIC, "value": val * n_total / 1e6, "unit": _bench.UNIT, "steps_per_s": val,
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True,
@@ -513,7 +516,8 @@ def bench_main(args):
                             "words, sharded step (halo exchange inside), device -> pinned-host copy back; max over ranks"},
             "gpu_launches": int(tot[2].item()),
             "roofline": roofline,
-            "stage_ms_slowest_rank": {"sort": float(roof_max[4].item()), "density": d_ms, "force_and_exchange": f_ms},
+            "stage_ms_slowest_rank": {"sort": float(roof_max[4].item()), "density": d_ms, "force": f_ms,
+                                      "exchange_on_comm_stream": float(roof_max[5].item())},
             "cpu_baseline": None,
             "notes": "cpu_baseline is reported by the N = 1 run and by --impl reference (bench.py contract)",
         }

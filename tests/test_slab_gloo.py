@@ -29,10 +29,11 @@ def test_plan_slabs_balanced_and_valid():
         slab.plan_slabs(np.ones(7), 2)
 
 
-def _run(nproc, port, extra, graph=False):
+def _run(nproc, port, extra, graph=False, split_density=False):
     import build_emu
     lib = build_emu.build()
-    env = dict(os.environ, SPH_EMU_LIB=lib, PYTHONPATH=ROOT, SPH_SHARD_GRAPH="1" if graph else "0")
+    env = dict(os.environ, SPH_EMU_LIB=lib, PYTHONPATH=ROOT, SPH_SHARD_GRAPH="1" if graph else "0",
+               SPH_SHARD_SPLIT_DENSITY="1" if split_density else "0")
     env.pop("SPH_B200_LIB", None)
     script = os.path.join(ROOT, "tools", "check_slab_parity.py")
     if nproc == 1:
@@ -58,8 +59,10 @@ def test_sharded_two_ranks_equal_the_single_engine():
 def test_three_ranks_skewed_cuts_are_rebalanced_on_the_device():
     """Deliberately skewed cuts, re-balancing every 2 steps: the cuts must move (decided on the device by both
     ranks of a cut from the exchanged headers), particles migrate, and the result still equals the single engine
-    (default mode: asynchronous un-graphed launches)."""
-    out = _run(3, 29548, ["--counts", "32", "8", "8", "--steps", "24", "--vx", "8", "--skew", "-2", "--rebalance-every", "2"])
+    (default mode: asynchronous un-graphed launches; the 8-rank sequence with the split density pass -- boundary
+    densities and forces first, the exchange behind the interior densities and forces)."""
+    out = _run(3, 29548, ["--counts", "32", "8", "8", "--steps", "24", "--vx", "8", "--skew", "-2", "--rebalance-every", "2"],
+               split_density=True)
     assert out["ok"] and out["same_particle_set"] and out["max_dx_over_d"] < 1e-4, out
     assert out["migrated"] and out["cuts_moved"], out
     first, last = out["owned_first_last"], None

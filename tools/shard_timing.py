@@ -61,6 +61,7 @@ if rank == 0:
     out = {"tag": a.tag, "scene": a.scene, "world": world, "ms_per_step": round(float(ms.item()), 4), "halo_cap": sim.halo_cap,
            "n_cap": sim.n_cap}
     out.update({k: round(float(v), 4) for k, v in zip(sorted(acc) + ["n_live_max", "owned_max"], t.tolist())})
+    out["split_density"] = os.environ.get("SPH_SHARD_SPLIT_DENSITY", "default")
     print(json.dumps(out), flush=True)
 dist.barrier()
 dist.destroy_process_group()
