@@ -1,19 +1,26 @@
 #!/bin/bash
-# Round-2 GPU call 19 (8 GPUs): box_16m, split density pass on (default at 8 ranks) vs off; bench line.
+# Round-2 GPU call 21 (1 GPU box, CPU work): OpenMP binding of the CPU reference arm: close vs spread vs unbound.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-N=8
-run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port $1 tools/shard_timing.py --scene box_16m --steps 40 --warm 25 "${@:2}" 2>&1 | grep "^{"; }
 {
-echo "== split density ON"; SPH_SHARD_SPLIT_DENSITY=1 run 29541 --tag split
-echo "== split density OFF"; SPH_SHARD_SPLIT_DENSITY=0 run 29542 --tag nosplit
-echo "== bench --gpus $N (20 / 5), default"
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N --master-addr 127.0.0.1 --master-port 29535 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_r02_n$N.json 2> gpurun_out/bench_r02_n$N.err; tail -c 300 gpurun_out/bench_r02_n$N.err; python - <<P
-import json
-try:
-    d=json.loads(open('gpurun_out/bench_r02_n$N.json').read().strip().splitlines()[-1])
-    for k in ('value','ms_per_step','parity_check','strong_scaling','halo','stage_ms_slowest_rank','e2e','clocks'): print(k, json.dumps(d.get(k))[:300])
-except Exception as e: print("bench parse failed", e, open('gpurun_out/bench_r02_n$N.json').read()[-800:])
+nproc; lscpu | grep -E "Model name|Socket|Core|Thread|NUMA" | head -8
+for bind in close spread false; do
+  echo "== OMP_PROC_BIND=$bind"
+  OMP_PROC_BIND=$bind OMP_PLACES=cores timeout 300 python bench.py --impl reference --steps 10 --warmup 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['steps_per_s'], d['cpu_baseline']['cores'], d['cpu_baseline']['threads_tried'])"
+done
+echo "== unset"; env -u OMP_PROC_BIND -u OMP_PLACES python - <<'P'
+import os, time, sys
+sys.path.insert(0, '.')
+os.environ.pop('OMP_PROC_BIND', None); os.environ.pop('OMP_PLACES', None)
+from oracle.sph_oracle import OracleSim, set_threads
+from sph_taichi_b200 import scene
+o = OracleSim(scene.dragon_bath()); o.initialize()
+for n in (128, 64, 32, 16):
+    set_threads(n); o.step(); t0 = time.perf_counter()
+    for _ in range(3): o.step()
+    print(n, 3 / (time.perf_counter() - t0))
 P
-} > gpurun_out/call19.log 2>&1
-tail -30 gpurun_out/call19.log
+} > gpurun_out/call21.log 2>&1
+tail -30 gpurun_out/call21.log
