@@ -208,13 +208,19 @@ class ClockSampler:
 
 def best_thread_count(o, reps=3):
     """Give the CPU arm its best shot: the pair loops are memory-latency bound and SMT siblings can hurt, so
-    time `reps` steps (after one untimed step) at cpu_count, /2 and /4 threads and keep the fastest.  Returns
+    time `reps` steps (after one untimed step) at cpu_count, /2, /4 and /8 threads (plus the cgroup CPU quota when the
+    box has one -- on this pool 128 threads run at 0.7 steps/s against 14 at 16-32, the signature of a quota well
+    below the visible thread count, see profiles/r02_cpu_arm_binding.txt) and keep the fastest.  Returns
     (best, {threads: steps/s}) -- round 1 timed ONE step per candidate and picked 32 threads on one box and 64 on
     another for the same scene (3.5x swing in the reference arm)."""
     from oracle.sph_oracle import set_threads
     total = os.cpu_count() or 1
     table = {}
-    for n in sorted({total, max(1, total // 2), max(1, total // 4)}, reverse=True):
+    cand = {total, max(1, total // 2), max(1, total // 4), max(1, total // 8)}
+    quota = cgroup_cpu_quota()
+    if quota:
+        cand.add(max(1, min(total, int(quota))))
+    for n in sorted(cand, reverse=True):
         set_threads(n)
         o.step()
         t0 = time.perf_counter()
@@ -226,10 +232,26 @@ def best_thread_count(o, reps=3):
     return best, table
 
 
+def cgroup_cpu_quota():
+    """CPUs the container may use per the cgroup-v2/v1 bandwidth controller (None = unlimited or unreadable)."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else float(q) / float(per)
+    except (OSError, ValueError):
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / per
+    except (OSError, ValueError):
+        return None
+
+
 def thread_note(best, table):
     ranked = sorted(table.items(), key=lambda kv: -kv[1])
+    quota = cgroup_cpu_quota()
     return (f"OpenMP (OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')}, OMP_PLACES={os.environ.get('OMP_PLACES')}) on {best} of "
-            f"{os.cpu_count()} host threads; candidates timed over 3 steps each: "
+            f"{os.cpu_count()} host threads (cgroup CPU quota: {quota if quota else 'none'}); candidates timed over 3 steps each: "
             + ", ".join(f"{n} thr {v:.1f} steps/s" for n, v in ranked))
 
 
