@@ -1,26 +1,14 @@
 #!/bin/bash
-# Round-2 GPU call 21 (1 GPU box, CPU work): OpenMP binding of the CPU reference arm: close vs spread vs unbound.
-cd "$(dirname "$0")/.."
+# per-call scratch script (GPU box): 2-GPU long run of the sharded engine + the final N = 2 bench line
 mkdir -p gpurun_out
-{
-nproc; lscpu | grep -E "Model name|Socket|Core|Thread|NUMA" | head -8
-for bind in close spread false; do
-  echo "== OMP_PROC_BIND=$bind"
-  OMP_PROC_BIND=$bind OMP_PLACES=cores timeout 300 python bench.py --impl reference --steps 10 --warmup 3 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['steps_per_s'], d['cpu_baseline']['cores'], d['cpu_baseline']['threads_tried'])"
-done
-echo "== unset"; env -u OMP_PROC_BIND -u OMP_PLACES python - <<'P'
-import os, time, sys
-sys.path.insert(0, '.')
-os.environ.pop('OMP_PROC_BIND', None); os.environ.pop('OMP_PLACES', None)
-from oracle.sph_oracle import OracleSim, set_threads
-from sph_taichi_b200 import scene
-o = OracleSim(scene.dragon_bath()); o.initialize()
-for n in (128, 64, 32, 16):
-    set_threads(n); o.step(); t0 = time.perf_counter()
-    for _ in range(3): o.step()
-    print(n, 3 / (time.perf_counter() - t0))
-P
-} > gpurun_out/call21.log 2>&1
-tail -30 gpurun_out/call21.log
+L=gpurun_out/call22.log
+: > $L
+echo "== sharded soak, 2 GPUs, 2 M particles, 3000 steps" >> $L
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 \
+  tools/check_slab_parity.py --counts 200 100 100 --steps 3000 --soak 250 >> $L 2>&1
+echo "rc=$?" >> $L
+echo "== bench N=2" >> $L
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29552 \
+  bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2_final.json 2>> $L
+echo "rc=$?" >> $L
+tail -c 1500 gpurun_out/bench_n2_final.json >> $L
