@@ -158,10 +158,20 @@ int sph_step(SphCtx *ctx, int32_t nsteps, void *stream);
  *   5 multiply_time_step(dfsph_factor, arg) (:229-233)
  *   6 divergence_solver_iteration_kernel (:278-290)   7 pressure_solve_iteration_kernel (:354-367)
  *   8 compute_non_pressure_forces (:92-101)   9 predict_velocity (:392-397)   10 advect (:104-111)
- * The convergence loops (divergence_solve, pressure_solve) stay on the host, as in the reference.
+ * With these ops the convergence loops (divergence_solve, pressure_solve) run on the host, as in the reference.
  * sph_set_dfsph(1) switches the density pass to DFSPH semantics (no clamp, no EOS). */
 int sph_set_dfsph(SphCtx *ctx, int32_t enable);
 int sph_dfsph_op(SphCtx *ctx, int32_t op, float arg, void *out_dev, void *stream);
+/* The Jacobi loop of divergence_solve (mode 0, DFSPH.py:245-254: sweeps of op 6 + op 2 + op 4 with offset 0) or of
+ * pressure_solve (mode 1, DFSPH.py:323-331: op 7 + op 3 + op 4 with offset density_0) with the loop condition
+ *     while m < 1 or m < max_iterations:  avg = sweep() / n_fluid;  if avg <= eta: break;  m += 1
+ * evaluated on the device after every sweep.  Sweeps are launched `first_batch` at a time (then in pairs); sweeps
+ * behind the converged one return immediately; the host waits once per batch instead of once per sweep.  The
+ * steps the reference performs before and after the loop (ops 2 / 3 and 5) stay with the caller.  SYNCHRONOUS:
+ * returns m (iterations_out), the sweeps executed and the last avg (host pointers, may be NULL). */
+int sph_dfsph_solve(SphCtx *ctx, int32_t mode, int32_t max_iterations, double eta, float offset, int64_t n_fluid,
+                    int32_t first_batch, int32_t *iterations_out, int32_t *sweeps_out, double *avg_err_out,
+                    void *stream);
 
 /* ---- x-slab sharding across the GPUs of one node (new; the reference is single-device) -------
  * One process per GPU.  Each rank owns the cell layers [x_lo, x_hi) of the x axis (x-major flattening,

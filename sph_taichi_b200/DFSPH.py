@@ -1,10 +1,17 @@
 """``DFSPHSolver`` (reference ``DFSPH.py:5-408``, simulationMethod 4): divergence-free SPH.
 
-Same method names, constants and host-side convergence loops as the reference; every kernel is one
-``sph_dfsph_op`` call on the CUDA engine (``csrc/sph_dfsph.cuh``).  The density pass builds the
-per-step neighbour lists that all DFSPH kernels walk.
+Same method names and constants as the reference; every kernel is one ``sph_dfsph_op`` call on the CUDA engine
+(``csrc/sph_dfsph.cuh``).  The density pass builds the per-step neighbour lists that all DFSPH kernels walk.
+
+The two convergence loops exist in both forms: ``device_side_loops = True`` (default) hands the Jacobi sweeps to
+``sph_dfsph_solve`` -- loop condition evaluated on the device after every sweep, one host wait per batch of sweeps,
+the first batch sized by the previous step's count; ``False`` runs the loops on the host as the reference writes
+them (``divergence_solver_iteration`` / ``pressure_solve_iteration``: one density-error read-back per sweep).  Same
+sweeps and same iteration counts either way (``tests/test_gpu_dfsph.py`` runs both against the oracle).
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
@@ -26,8 +33,10 @@ class DFSPHSolver(SPHBase):
         self.max_error_V = 0.1
         self.max_error = 0.05
         self.verbose = False
+        self.device_side_loops = os.environ.get("SPH_DFSPH_HOST_LOOPS", "0") in ("", "0")  # A/B switch
         self.last_iterations_v = 0
         self.last_iterations = 0
+        self._sweeps_guess = [2, 3]  # first batch of the next divergence / pressure solve (updated every step)
         self.ps._engine.set_dfsph(True)
         self._err = torch.zeros(1, dtype=torch.float64, device=self.ps.device)
 
@@ -74,7 +83,15 @@ class DFSPHSolver(SPHBase):
     def advect(self):
         self._op(OP_ADVECT)
 
-    # ---- host loops (DFSPH.py:236-276, 314-352) -----------------------------------------------
+    def _solve_on_device(self, mode, max_iterations, eta, offset):
+        self.ps._push()
+        it, sweeps, avg = self.ps._engine.dfsph_solve(mode, max_iterations, eta, offset, self.ps.fluid_particle_num,
+                                                      self._sweeps_guess[mode])
+        self.ps._after_engine()
+        self._sweeps_guess[mode] = max(1, sweeps)
+        return it, avg
+
+    # ---- convergence loops (DFSPH.py:236-276, 314-352) ----------------------------------------
     def divergence_solver_iteration(self):
         self.divergence_solver_iteration_kernel()
         self.compute_density_change()
@@ -87,12 +104,16 @@ class DFSPHSolver(SPHBase):
         self.multiply_time_step(self.ps.dfsph_factor, inv_dt)
         m_iterations_v = 0
         avg_density_err = 0.0
-        while m_iterations_v < 1 or m_iterations_v < self.m_max_iterations_v:
-            avg_density_err = self.divergence_solver_iteration()
+        if self.device_side_loops:
             eta = 1.0 / self.dt[None] * self.max_error_V * 0.01 * self.density_0
-            if avg_density_err <= eta:
-                break
-            m_iterations_v += 1
+            m_iterations_v, avg_density_err = self._solve_on_device(0, self.m_max_iterations_v, eta, 0.0)
+        else:
+            while m_iterations_v < 1 or m_iterations_v < self.m_max_iterations_v:
+                avg_density_err = self.divergence_solver_iteration()
+                eta = 1.0 / self.dt[None] * self.max_error_V * 0.01 * self.density_0
+                if avg_density_err <= eta:
+                    break
+                m_iterations_v += 1
         if self.verbose:
             print(f"DFSPH - iteration V: {m_iterations_v} Avg density err: {avg_density_err}")
         self.multiply_time_step(self.ps.dfsph_factor, self.dt[None])
@@ -110,12 +131,16 @@ class DFSPHSolver(SPHBase):
         self.multiply_time_step(self.ps.dfsph_factor, inv_dt2)
         m_iterations = 0
         avg_density_err = 0.0
-        while m_iterations < 1 or m_iterations < self.m_max_iterations:
-            avg_density_err = self.pressure_solve_iteration()
+        if self.device_side_loops:
             eta = self.max_error * 0.01 * self.density_0
-            if avg_density_err <= eta:
-                break
-            m_iterations += 1
+            m_iterations, avg_density_err = self._solve_on_device(1, self.m_max_iterations, eta, self.density_0)
+        else:
+            while m_iterations < 1 or m_iterations < self.m_max_iterations:
+                avg_density_err = self.pressure_solve_iteration()
+                eta = self.max_error * 0.01 * self.density_0
+                if avg_density_err <= eta:
+                    break
+                m_iterations += 1
         if self.verbose:
             print(f"DFSPH - iterations: {m_iterations} Avg density Err: {avg_density_err:.4f}")
         self.last_iterations = m_iterations

@@ -1067,8 +1067,8 @@ int sph_dfsph_op(SphCtx *ctx, int32_t op, float arg, void *out_dev, void *stream
             k_dfsph_density_error<<<b256, 256, 0, st>>>(P, ctx->S, arg, static_cast<double *>(out_dev));
             break;
         case DFSPH_MULTIPLY_FACTOR: k_dfsph_multiply_factor<<<b256, 256, 0, st>>>(P, ctx->S, arg); break;
-        case DFSPH_DIVERGENCE_ITERATION: k_dfsph_iteration<0><<<b128, 128, 0, st>>>(P, ctx->S); break;
-        case DFSPH_PRESSURE_ITERATION: k_dfsph_iteration<1><<<b128, 128, 0, st>>>(P, ctx->S); break;
+        case DFSPH_DIVERGENCE_ITERATION: k_dfsph_iteration<0><<<b128, 128, 0, st>>>(P, ctx->S, nullptr); break;
+        case DFSPH_PRESSURE_ITERATION: k_dfsph_iteration<1><<<b128, 128, 0, st>>>(P, ctx->S, nullptr); break;
         case DFSPH_NON_PRESSURE_FORCES: k_dfsph_non_pressure<<<b128, 128, 0, st>>>(P, ctx->S); break;
         case DFSPH_PREDICT_VELOCITY: k_dfsph_predict_velocity<<<b256, 256, 0, st>>>(P, ctx->S); break;
         case DFSPH_ADVECT:
@@ -1079,6 +1079,48 @@ int sph_dfsph_op(SphCtx *ctx, int32_t op, float arg, void *out_dev, void *stream
     }
     if (op != DFSPH_COMPUTE_DENSITIES) ctx->launches += 1;
     CUDA_TRY(ctx, cudaGetLastError());
+    return SPH_OK;
+}
+
+// The Jacobi loop of divergence_solve (mode 0, DFSPH.py:245-254) or pressure_solve (mode 1, DFSPH.py:323-331) with the
+// loop condition on the device: sweeps are launched in batches (the first as long as the caller expects the loop to
+// run -- the previous step's count is a good guess), every sweep ends with k_dfsph_check, sweeps behind the
+// converged one return at once, and the host reads the control block once per batch.
+int sph_dfsph_solve(SphCtx *ctx, int32_t mode, int32_t max_iterations, double eta, float offset, int64_t n_fluid,
+                    int32_t first_batch, int32_t *iterations_out, int32_t *sweeps_out, double *avg_err_out, void *stream) {
+    if (!ctx || (mode != 0 && mode != 1) || n_fluid < 1) return SPH_E_ARG;
+    if (!ctx->P.dfsph) return fail(ctx, SPH_E_ARG, "sph_set_dfsph(1) was not called");
+    if (!ctx->built || !ctx->list_valid)
+        return fail(ctx, SPH_E_ARG, "neighbour lists are stale: run sph_neighbor_build and op 0 (compute_densities) first");
+    const DevParams &P = ctx->P;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DfsphCtrl *ctrl = reinterpret_cast<DfsphCtrl *>(ctx->ws + ctx->L.off_scratch);
+    DfsphCtrl h{};
+    CUDA_TRY(ctx, cudaMemsetAsync(ctrl, 0, sizeof(DfsphCtrl), st));
+    if (P.n > 0) {
+        const int b128 = blocks_for(P.n, 128);
+        int batch = std::max(1, std::min(first_batch, 64));
+        while (!h.done) {
+            for (int s = 0; s < batch; ++s) {
+                if (mode == 0) {
+                    k_dfsph_iteration<0><<<b128, 128, 0, st>>>(P, ctx->S, ctrl);
+                    k_dfsph_density_change_err<0><<<b128, 128, 0, st>>>(P, ctx->S, offset, ctrl);
+                } else {
+                    k_dfsph_iteration<1><<<b128, 128, 0, st>>>(P, ctx->S, ctrl);
+                    k_dfsph_density_change_err<1><<<b128, 128, 0, st>>>(P, ctx->S, offset, ctrl);
+                }
+                k_dfsph_check<<<1, 1, 0, st>>>(ctrl, (double)n_fluid, eta, max_iterations);
+            }
+            ctx->launches += 3 * (int64_t)batch;
+            CUDA_TRY(ctx, cudaGetLastError());
+            CUDA_TRY(ctx, cudaMemcpyAsync(&h, ctrl, sizeof(DfsphCtrl), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            batch = 2;  // the guess was short: continue in pairs
+        }
+    }
+    if (iterations_out) *iterations_out = h.iterations;
+    if (sweeps_out) *sweeps_out = h.sweeps;
+    if (avg_err_out) *avg_err_out = h.last_avg;
     return SPH_OK;
 }
 

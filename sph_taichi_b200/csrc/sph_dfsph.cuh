@@ -2,9 +2,12 @@
 // sorted SoA state and per-step neighbour lists as the WCSPH path.
 //
 // compute_densities (DFSPH.py:39-47) is k_density_tma in DFSPH mode (no clamp, no EOS); it also
-// builds the neighbour lists that every kernel below walks.  The host-side convergence loops
-// (divergence_solve / pressure_solve, DFSPH.py:236-276, 314-352) stay in the Python shell like in
-// the reference; each kernel here is one reference @ti.kernel.
+// builds the neighbour lists that every kernel below walks.  Each kernel here is one reference @ti.kernel.
+// The convergence loops (divergence_solve / pressure_solve, DFSPH.py:236-276, 314-352) exist twice: in the Python
+// shell exactly as the reference writes them (one density-error read-back per Jacobi sweep), and as
+// sph_dfsph_solve: the sweeps of a batch are launched back to back, the loop condition is evaluated ON THE
+// DEVICE by k_dfsph_check after every sweep (DfsphCtrl), and the sweeps behind the converged one return at once --
+// same sweeps, same iteration counts, one read-back per batch instead of one per sweep.
 #pragma once
 #include "sph_kernels.cuh"
 
@@ -20,6 +23,16 @@ enum DfsphOp {
     DFSPH_NON_PRESSURE_FORCES = 8, // DFSPH.py:92-101
     DFSPH_PREDICT_VELOCITY = 9,    // DFSPH.py:392-397
     DFSPH_ADVECT = 10,             // DFSPH.py:104-111
+};
+
+// Device-resident state of one convergence loop (sph_dfsph_solve); lives in the workspace scratch block.
+struct DfsphCtrl {
+    double err;          // running sum of (rho0 * density_adv - offset) of the current sweep
+    double last_avg;     // avg_density_err of the last evaluated sweep
+    int32_t iterations;  // the reference's m_iterations(_v): sweeps that did NOT meet eta
+    int32_t done;        // loop left (converged, or the iteration cap reached)
+    int32_t sweeps;      // sweeps actually executed
+    int32_t pad;
 };
 
 // Dense walk over the neighbour list of particle i (reference visiting order), gathers batched by
@@ -84,10 +97,7 @@ __global__ void __launch_bounds__(128) k_dfsph_factor(DevParams P, DevArrays S) 
 
 // MODE 0: compute_density_change (DFSPH.py:157-196);  MODE 1: compute_density_adv (DFSPH.py:198-219)
 template <int MODE>
-__global__ void __launch_bounds__(128) k_dfsph_density_change(DevParams P, DevArrays S) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t fl;
-    if (!dfsph_fluid(P, S, i, fl)) return;
+__device__ __forceinline__ float dfsph_density_change_of(const DevParams &P, const DevArrays &S, int i) {
     float4 pi = S.posm[i];
     float4 vi = S.veld[i];
     float acc = 0.f;
@@ -106,25 +116,65 @@ __global__ void __launch_bounds__(128) k_dfsph_density_change(DevParams P, DevAr
         da = fmaxf(vi.w / P.rho0 + P.dt * acc, 1.0f);
     }
     S.dfs[i].y = da;
+    return da;
+}
+template <int MODE>
+__global__ void __launch_bounds__(128) k_dfsph_density_change(DevParams P, DevArrays S) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t fl;
+    if (!dfsph_fluid(P, S, i, fl)) return;
+    dfsph_density_change_of<MODE>(P, S, i);
 }
 
-// DFSPH.py:221-227
-__global__ void __launch_bounds__(256) k_dfsph_density_error(DevParams P, DevArrays S, float offset, double *out) {
-    __shared__ double red[8];
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double e = 0.0;
-    uint32_t fl;
-    if (dfsph_fluid(P, S, i, fl)) e = (double)(P.rho0 * S.dfs[i].y - offset);
+// block-wide fp64 sum -> one atomic per CTA (DFSPH.py:221-227 returns the sum to the host)
+template <int WARPS>
+__device__ __forceinline__ void dfsph_block_sum_to(double e, double *out) {
+    __shared__ double red[WARPS];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
     __syncthreads();
     if (threadIdx.x < 32) {
-        double t = threadIdx.x < 8 ? red[threadIdx.x] : 0.0;
+        double t = threadIdx.x < WARPS ? red[threadIdx.x] : 0.0;
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
         if (threadIdx.x == 0) atomicAdd(out, t);
     }
+}
+
+// One sweep of sph_dfsph_solve = k_dfsph_iteration + this kernel + k_dfsph_check: the density change / advected
+// density of the sweep and its error sum in ONE pass (the host loop runs compute_density_error as a second kernel).
+template <int MODE>
+__global__ void __launch_bounds__(128) k_dfsph_density_change_err(DevParams P, DevArrays S, float offset, DfsphCtrl *ctrl) {
+    if (ctrl->done) return;  // written only by k_dfsph_check, between kernels: uniform over the grid
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t fl;
+    double e = 0.0;
+    if (dfsph_fluid(P, S, i, fl)) e = (double)(P.rho0 * dfsph_density_change_of<MODE>(P, S, i) - offset);
+    dfsph_block_sum_to<4>(e, &ctrl->err);
+}
+
+// The loop condition of divergence_solve / pressure_solve (DFSPH.py:245-254, 323-331), evaluated on the device:
+//   while m < 1 or m < max_iterations:  avg = sweep();  if avg <= eta: break;  m += 1
+__global__ void k_dfsph_check(DfsphCtrl *ctrl, double n_fluid, double eta, int32_t max_iterations) {
+    if (ctrl->done) return;
+    const double avg = ctrl->err / n_fluid;
+    ctrl->last_avg = avg;
+    ctrl->err = 0.0;
+    ctrl->sweeps += 1;
+    if (avg <= eta) { ctrl->done = 1; return; }
+    const int32_t m = ctrl->iterations + 1;
+    ctrl->iterations = m;
+    if (!(m < 1 || m < max_iterations)) ctrl->done = 1;
+}
+
+// DFSPH.py:221-227
+__global__ void __launch_bounds__(256) k_dfsph_density_error(DevParams P, DevArrays S, float offset, double *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    uint32_t fl;
+    if (dfsph_fluid(P, S, i, fl)) e = (double)(P.rho0 * S.dfs[i].y - offset);
+    dfsph_block_sum_to<8>(e, out);
 }
 
 // DFSPH.py:229-233 applied to dfsph_factor
@@ -139,7 +189,8 @@ __global__ void k_dfsph_multiply_factor(DevParams P, DevArrays S, float ts) {
 // (DFSPH.py:354-389).  The reactions MODE 0 would add to dynamic rigid particles are overwritten by
 // compute_non_pressure_forces before anything reads them (DFSPH.py:402), so only MODE 1 scatters them.
 template <int MODE>
-__global__ void __launch_bounds__(128) k_dfsph_iteration(DevParams P, DevArrays S) {
+__global__ void __launch_bounds__(128) k_dfsph_iteration(DevParams P, DevArrays S, const DfsphCtrl *ctrl) {
+    if (ctrl && ctrl->done) return;  // sph_dfsph_solve: a sweep launched behind the converged one
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t fl;
     if (!dfsph_fluid(P, S, i, fl)) return;

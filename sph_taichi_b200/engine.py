@@ -197,6 +197,15 @@ class Engine:
         self._check(self.lib.sph_dfsph_op(self.ctx, int(op), float(arg), None if out is None else out.data_ptr(),
                                           self._stream()), "sph_dfsph_op")
 
+    def dfsph_solve(self, mode, max_iterations, eta, offset, n_fluid, first_batch):
+        """The Jacobi loop of divergence_solve (mode 0) / pressure_solve (mode 1) with the loop condition on the
+        device; returns (iterations, sweeps, last avg_density_err).  Synchronous (one wait per batch of sweeps)."""
+        it, sw, avg = C.c_int32(0), C.c_int32(0), C.c_double(0.0)
+        self._check(self.lib.sph_dfsph_solve(self.ctx, int(mode), int(max_iterations), float(eta), float(offset),
+                                             int(n_fluid), int(first_batch), C.byref(it), C.byref(sw), C.byref(avg),
+                                             self._stream()), "sph_dfsph_solve")
+        return int(it.value), int(sw.value), float(avg.value)
+
     def step(self, nsteps=1):
         self._check(self.lib.sph_step(self.ctx, int(nsteps), self._stream()), "sph_step")
 

@@ -96,10 +96,14 @@ def test_dfsph_kernels_on_overfull_neighbour_lists():
     assert _maxrel(ps.v.to_numpy(), o.v) < 5 * REL
 
 
-def test_dfsph_steps_vs_oracle():
+@pytest.mark.parametrize("device_side_loops", [True, False])
+def test_dfsph_steps_vs_oracle(device_side_loops):
+    """Whole steps against the oracle, with the Jacobi loops run by sph_dfsph_solve (loop condition on the device,
+    the default) and by the reference-structured host loops."""
     from sph_taichi_b200 import scene
     sc = _dfsph(scene.dam_break_box([16, 20, 16], domain_end=[0.8, 0.8, 0.6], start=[0.06, 0.06, 0.06]))
     o, ps, s = _pair(sc)
+    s.device_side_loops = device_side_loops
     o.initialize(); s.initialize()
     counts_o, counts_g = [], []
     for _ in range(45):
@@ -114,6 +118,26 @@ def test_dfsph_steps_vs_oracle():
     assert err < (2e-3 if same else 5e-2), (err, same, counts_o[-5:], counts_g[-5:])
     rho = ps.density.to_numpy()
     assert np.isfinite(rho).all() and rho.max() < 1400.0
+
+
+def test_device_side_loops_run_the_same_sweeps_as_the_host_loops():
+    """sph_dfsph_solve only moves the loop condition: same sweeps, same counts, bit-identical state."""
+    from sph_taichi_b200 import scene
+    sc = _dfsph(scene.dam_break_box([14, 18, 12], domain_end=[0.8, 0.8, 0.6], start=[0.06, 0.06, 0.06]))
+    runs = []
+    for dev_loops in (True, False):
+        _, ps, s = _pair(sc, seed=11, amp=0.002, squeeze=0.9)  # rho > rho0 from the start: both solvers iterate at once
+        s.device_side_loops = dev_loops
+        s.initialize()
+        counts = []
+        for _ in range(8):
+            s.step()
+            counts.append((s.last_iterations_v, s.last_iterations))
+        assert ps._engine.check_status() == 0
+        runs.append((counts, ps.x.to_numpy().copy(), ps.v.to_numpy().copy()))
+    assert runs[0][0] == runs[1][0]
+    assert max(c[1] for c in runs[0][0]) >= 2 and max(c[0] for c in runs[0][0]) >= 1  # both loops really iterated
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
 
 
 def test_dfsph_dragon_bath_full_size_invariants():

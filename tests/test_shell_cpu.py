@@ -30,6 +30,10 @@ class RecordingEngine:
             return None
         return f
 
+    def dfsph_solve(self, mode, max_iterations, eta, offset, n_fluid, first_batch):
+        self.log.append(f"dfsph_solve:{mode}:{first_batch}")
+        return 2, 3, 0.5 * eta
+
     def dfsph_op(self, op, arg=0.0, out=None):
         self.log.append(f"dfsph:{op}")
         if op == 4 and out is not None:   # density error: converge after three sweeps
@@ -143,6 +147,19 @@ def test_dfsph_host_loops(fake_engine):
     assert isinstance(s, DFSPHSolver) and hasattr(ps, "dfsph_factor") and hasattr(ps, "density_adv")
     s.initialize()
     eng = RecordingEngine.last
+    # default: the sweeps run in sph_dfsph_solve (loop condition on the device); what the reference does before
+    # and after the loop stays in the shell, and the sweep count of one solve sizes the first batch of the next
+    assert s.device_side_loops
+    eng.log.clear()
+    s.divergence_solve()
+    assert eng.log == ["dfsph:2", "dfsph:5", "dfsph_solve:0:2", "dfsph:5"] and s.last_iterations_v == 2
+    eng.log.clear()
+    s.pressure_solve()
+    s.pressure_solve()
+    assert [c for c in eng.log if c.startswith("dfsph_solve")] == ["dfsph_solve:1:3", "dfsph_solve:1:3"]
+    assert s.last_iterations == 2
+    # the reference's own loop structure: one density-error read-back per sweep
+    s.device_side_loops = False
     eng.log.clear()
     eng._err = 1.0e9
     s.divergence_solve()

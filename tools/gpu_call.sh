@@ -1,14 +1,27 @@
 #!/bin/bash
-# per-call scratch script (GPU box): 2-GPU long run of the sharded engine + the final N = 2 bench line
+# per-call scratch script (GPU box): final check of the tree + DFSPH with the loop condition on the device vs on the host
 mkdir -p gpurun_out
-L=gpurun_out/call22.log
+L=gpurun_out/call23.log
 : > $L
-echo "== sharded soak, 2 GPUs, 2 M particles, 3000 steps" >> $L
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 \
-  tools/check_slab_parity.py --counts 200 100 100 --steps 3000 --soak 250 >> $L 2>&1
+echo "== pytest gpu" >> $L
+timeout 900 python -m pytest tests -x -q -m gpu >> $L 2>&1
 echo "rc=$?" >> $L
-echo "== bench N=2" >> $L
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29552 \
-  bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2_final.json 2>> $L
+echo "== smoke" >> $L
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" >> $L 2>&1
 echo "rc=$?" >> $L
-tail -c 1500 gpurun_out/bench_n2_final.json >> $L
+export SPH_BENCH_CPU_BUDGET_S=4 SPH_BENCH_SKIP_EXTRA=1
+echo "== DFSPH dragon_bath_dfsph, loop condition on the device" >> $L
+timeout 400 python bench.py --scene dragon_bath_dfsph --steps 60 --warmup 20 > gpurun_out/bench_dfsph_device_loops.json 2>> $L
+echo "rc=$?" >> $L
+echo "== DFSPH dragon_bath_dfsph, host loops (reference structure)" >> $L
+SPH_DFSPH_HOST_LOOPS=1 timeout 400 python bench.py --scene dragon_bath_dfsph --steps 60 --warmup 20 > gpurun_out/bench_dfsph_host_loops.json 2>> $L
+echo "rc=$?" >> $L
+python - >> $L 2>&1 <<'P'
+import json
+for f in ("device_loops", "host_loops"):
+    try:
+        d = json.loads([l for l in open(f"gpurun_out/bench_dfsph_{f}.json") if l.startswith("{")][-1])
+        print(f, "ms/step", round(d["ms_per_step"], 4), "steady", round(d["steady"]["ms_per_step"], 4), "launches", d["gpu_launches"])
+    except Exception as e:
+        print(f, "failed", e)
+P
