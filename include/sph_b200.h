@@ -173,6 +173,25 @@ int sph_dfsph_solve(SphCtx *ctx, int32_t mode, int32_t max_iterations, double et
                     int32_t first_batch, int32_t *iterations_out, int32_t *sweeps_out, double *avg_err_out,
                     void *stream);
 
+/* One whole SPHBase.step() of the DFSPH solver (sph_base.py:263-271 with DFSPH.substep, DFSPH.py:399-408): neighbour
+ * build, moving boundary volumes, compute_densities, compute_DFSPH_factor, divergence_solve (if enabled),
+ * compute_non_pressure_forces, predict_velocity, pressure_solve, advect, solve_rigid_body, enforce_boundary_3D(fluid)
+ * -- every kernel launched from this one call, the two Jacobi loops run as in sph_dfsph_solve.  A DFSPH step is
+ * ~50 short launches; driven op by op from Python the HOST is the bottleneck (2.0 ms per step on dragon_bath_dfsph
+ * against 0.9 ms of kernels).  The caller fills the constants exactly as the reference's host code computes them. */
+typedef struct SphDfsphStep {
+    int32_t enable_divergence_solver;   /* DFSPH.py:12 */
+    int32_t max_iterations_v, max_iterations; /* m_max_iterations_v, m_max_iterations */
+    double eta_v, eta;                  /* 1/dt * max_error_V * 0.01 * density_0 ; max_error * 0.01 * density_0 */
+    float inv_dt, dt, inv_dt2;          /* the three factors multiply_time_step is called with (DFSPH.py:240, 262, 320) */
+    float density0;                     /* offset of the pressure loop's density error (DFSPH.py:317) */
+    int64_t n_fluid;                    /* fluid_particle_num (the error sums are averaged over it) */
+    int32_t first_batch_v, first_batch; /* in: sweeps launched before the first wait; out: sweeps the last step's loops ran */
+    int32_t iterations_v, iterations;   /* out: m_iterations_v, m_iterations of the last step */
+    double avg_err_v, avg_err;          /* out: the last avg_density_err of each loop */
+} SphDfsphStep;
+int sph_dfsph_step(SphCtx *ctx, int32_t nsteps, SphDfsphStep *io, void *stream);
+
 /* ---- x-slab sharding across the GPUs of one node (new; the reference is single-device) -------
  * One process per GPU.  Each rank owns the cell layers [x_lo, x_hi) of the x axis (x-major flattening,
  * particle_system.py:292-294: after the sort every layer is ONE contiguous index range) and keeps

@@ -3,11 +3,17 @@
 Same method names and constants as the reference; every kernel is one ``sph_dfsph_op`` call on the CUDA engine
 (``csrc/sph_dfsph.cuh``).  The density pass builds the per-step neighbour lists that all DFSPH kernels walk.
 
-The two convergence loops exist in both forms: ``device_side_loops = True`` (default) hands the Jacobi sweeps to
-``sph_dfsph_solve`` -- loop condition evaluated on the device after every sweep, one host wait per batch of sweeps,
-the first batch sized by the previous step's count; ``False`` runs the loops on the host as the reference writes
-them (``divergence_solver_iteration`` / ``pressure_solve_iteration``: one density-error read-back per sweep).  Same
-sweeps and same iteration counts either way (``tests/test_gpu_dfsph.py`` runs both against the oracle).
+Two ways to run it, same sweeps, same iteration counts, bit-identical state (``tests/test_gpu_dfsph.py`` runs both
+against the oracle):
+
+* ``device_side_loops = True`` (default): ``step()`` is ONE library call (``sph_dfsph_step``) that launches the
+  ~50 kernels of a step back to back and runs the two Jacobi loops with the loop condition evaluated on the device
+  after every sweep -- one host wait per batch of sweeps, the first batch sized by the previous step's count.  Driven
+  op by op from Python the host is the bottleneck (2.0 ms per step on dragon_bath_dfsph for 0.9 ms of kernels).
+  ``divergence_solve()`` / ``pressure_solve()`` called on their own use ``sph_dfsph_solve`` for the loop.
+* ``False`` (or ``SPH_DFSPH_HOST_LOOPS=1``): the reference's structure -- every method below is one launch and the
+  loops run on the host (``divergence_solver_iteration`` / ``pressure_solve_iteration``: one density-error read-back
+  per sweep).
 """
 from __future__ import annotations
 
@@ -144,6 +150,33 @@ class DFSPHSolver(SPHBase):
         if self.verbose:
             print(f"DFSPH - iterations: {m_iterations} Avg density Err: {avg_density_err:.4f}")
         self.last_iterations = m_iterations
+
+    def step(self, n=1):
+        """sph_base.py:263-271.  With device-side loops the whole step is one library call."""
+        if not self.device_side_loops:
+            return super().step(n)
+        from ._lib import SphDfsphStep
+        ps = self.ps
+        dt = self.dt[None]
+        io = SphDfsphStep(enable_divergence_solver=int(bool(self.enable_divergence_solver)),
+                          max_iterations_v=int(self.m_max_iterations_v), max_iterations=int(self.m_max_iterations),
+                          eta_v=1.0 / dt * self.max_error_V * 0.01 * self.density_0,
+                          eta=self.max_error * 0.01 * self.density_0,
+                          inv_dt=1 / dt, dt=dt, inv_dt2=1 / (dt * dt), density0=self.density_0,
+                          n_fluid=int(ps.fluid_particle_num), first_batch_v=self._sweeps_guess[0],
+                          first_batch=self._sweeps_guess[1])
+        ps._push()
+        ps._engine.dfsph_step(n, io)
+        ps._after_engine()
+        self._sweeps_guess = [int(io.first_batch_v), int(io.first_batch)]
+        self.last_iterations_v, self.last_iterations = int(io.iterations_v), int(io.iterations)
+        if self.verbose:
+            print(f"DFSPH - iteration V: {self.last_iterations_v} Avg density err: {io.avg_err_v}")
+            print(f"DFSPH - iterations: {self.last_iterations} Avg density Err: {io.avg_err:.4f}")
+        if ps.cfg.get_cfg("exportObj"):
+            for oid in ps._body_index:
+                if "restPosition" in ps.object_collection[oid]:
+                    self._update_mesh(oid)
 
     def substep(self):
         self.compute_densities()

@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "sph_boundary_volume", "sph_compute_densities", "sph_compute_non_pressure_forces", "sph_compute_pressure_forces",
     "sph_advect", "sph_enforce_boundary", "sph_set_rigid_bodies", "sph_compute_com", "sph_compute_rigid_rest_cm",
     "sph_solve_constraints", "sph_get_rigid_state", "sph_step", "sph_read_status", "sph_clear_status", "sph_neighbor_stats", "sph_particle_count",
-    "sph_launch_count", "sph_profile_step", "sph_timer_name", "sph_state_offsets", "sph_set_dfsph", "sph_dfsph_op", "sph_dfsph_solve",
+    "sph_launch_count", "sph_profile_step", "sph_timer_name", "sph_state_offsets", "sph_set_dfsph", "sph_dfsph_op", "sph_dfsph_solve", "sph_dfsph_step",
     "sph_comm_unique_id", "sph_comm_init_nccl", "sph_comm_set_transport", "sph_shard_configure", "sph_shard_begin",
     "sph_shard_step", "sph_halo_exchange", "sph_shard_info", "sph_shard_profile_step",
 ]
@@ -80,6 +80,14 @@ class SphTransport(C.Structure):
 class SphRigidBody(C.Structure):
     _fields_ = [("object_id", C.c_int32), ("solid_begin", C.c_int32), ("solid_end", C.c_int32),
                 ("rest_cm", C.c_float * 3)]
+
+
+class SphDfsphStep(C.Structure):
+    _fields_ = [("enable_divergence_solver", C.c_int32), ("max_iterations_v", C.c_int32), ("max_iterations", C.c_int32),
+                ("eta_v", C.c_double), ("eta", C.c_double), ("inv_dt", C.c_float), ("dt", C.c_float),
+                ("inv_dt2", C.c_float), ("density0", C.c_float), ("n_fluid", C.c_int64),
+                ("first_batch_v", C.c_int32), ("first_batch", C.c_int32), ("iterations_v", C.c_int32),
+                ("iterations", C.c_int32), ("avg_err_v", C.c_double), ("avg_err", C.c_double)]
 
 
 _lib = None
@@ -139,6 +147,7 @@ def load():
         "sph_dfsph_op": (C.c_int, [vp, i32, C.c_float, vp, vp]),
         "sph_dfsph_solve": (C.c_int, [vp, i32, i32, C.c_double, C.c_float, i64, i32, C.POINTER(i32), C.POINTER(i32),
                                       C.POINTER(C.c_double), vp]),
+        "sph_dfsph_step": (C.c_int, [vp, i32, C.POINTER(SphDfsphStep), vp]),
         "sph_comm_unique_id": (C.c_int, [C.c_char_p]),
         "sph_comm_init_nccl": (C.c_int, [vp, C.c_char_p, i32, i32]),
         "sph_comm_set_transport": (C.c_int, [vp, C.POINTER(SphTransport), i32, i32]),

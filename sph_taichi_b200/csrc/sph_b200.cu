@@ -1082,45 +1082,107 @@ int sph_dfsph_op(SphCtx *ctx, int32_t op, float arg, void *out_dev, void *stream
     return SPH_OK;
 }
 
+}  // extern "C"
+namespace {
+
 // The Jacobi loop of divergence_solve (mode 0, DFSPH.py:245-254) or pressure_solve (mode 1, DFSPH.py:323-331) with the
 // loop condition on the device: sweeps are launched in batches (the first as long as the caller expects the loop to
 // run -- the previous step's count is a good guess), every sweep ends with k_dfsph_check, sweeps behind the
 // converged one return at once, and the host reads the control block once per batch.
+int dfsph_solve_loop(SphCtx *ctx, int mode, int32_t max_iterations, double eta, float offset, int64_t n_fluid,
+                     int32_t first_batch, DfsphCtrl *h, cudaStream_t st) {
+    const DevParams &P = ctx->P;
+    DfsphCtrl *ctrl = reinterpret_cast<DfsphCtrl *>(ctx->ws + ctx->L.off_scratch);
+    *h = DfsphCtrl{};
+    CUDA_TRY(ctx, cudaMemsetAsync(ctrl, 0, sizeof(DfsphCtrl), st));
+    if (P.n == 0) return SPH_OK;
+    const int b128 = blocks_for(P.n, 128);
+    int batch = std::max(1, std::min(first_batch, 64));
+    while (!h->done) {
+        for (int s = 0; s < batch; ++s) {
+            if (mode == 0) {
+                k_dfsph_iteration<0><<<b128, 128, 0, st>>>(P, ctx->S, ctrl);
+                k_dfsph_density_change_err<0><<<b128, 128, 0, st>>>(P, ctx->S, offset, ctrl);
+            } else {
+                k_dfsph_iteration<1><<<b128, 128, 0, st>>>(P, ctx->S, ctrl);
+                k_dfsph_density_change_err<1><<<b128, 128, 0, st>>>(P, ctx->S, offset, ctrl);
+            }
+            k_dfsph_check<<<1, 1, 0, st>>>(ctrl, (double)n_fluid, eta, max_iterations);
+        }
+        ctx->launches += 3 * (int64_t)batch;
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaMemcpyAsync(h, ctrl, sizeof(DfsphCtrl), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        batch = 2;  // the guess was short: continue in pairs
+    }
+    return SPH_OK;
+}
+
+}  // namespace
+extern "C" {
+
 int sph_dfsph_solve(SphCtx *ctx, int32_t mode, int32_t max_iterations, double eta, float offset, int64_t n_fluid,
                     int32_t first_batch, int32_t *iterations_out, int32_t *sweeps_out, double *avg_err_out, void *stream) {
     if (!ctx || (mode != 0 && mode != 1) || n_fluid < 1) return SPH_E_ARG;
     if (!ctx->P.dfsph) return fail(ctx, SPH_E_ARG, "sph_set_dfsph(1) was not called");
     if (!ctx->built || !ctx->list_valid)
         return fail(ctx, SPH_E_ARG, "neighbour lists are stale: run sph_neighbor_build and op 0 (compute_densities) first");
-    const DevParams &P = ctx->P;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    DfsphCtrl *ctrl = reinterpret_cast<DfsphCtrl *>(ctx->ws + ctx->L.off_scratch);
     DfsphCtrl h{};
-    CUDA_TRY(ctx, cudaMemsetAsync(ctrl, 0, sizeof(DfsphCtrl), st));
-    if (P.n > 0) {
-        const int b128 = blocks_for(P.n, 128);
-        int batch = std::max(1, std::min(first_batch, 64));
-        while (!h.done) {
-            for (int s = 0; s < batch; ++s) {
-                if (mode == 0) {
-                    k_dfsph_iteration<0><<<b128, 128, 0, st>>>(P, ctx->S, ctrl);
-                    k_dfsph_density_change_err<0><<<b128, 128, 0, st>>>(P, ctx->S, offset, ctrl);
-                } else {
-                    k_dfsph_iteration<1><<<b128, 128, 0, st>>>(P, ctx->S, ctrl);
-                    k_dfsph_density_change_err<1><<<b128, 128, 0, st>>>(P, ctx->S, offset, ctrl);
-                }
-                k_dfsph_check<<<1, 1, 0, st>>>(ctrl, (double)n_fluid, eta, max_iterations);
-            }
-            ctx->launches += 3 * (int64_t)batch;
-            CUDA_TRY(ctx, cudaGetLastError());
-            CUDA_TRY(ctx, cudaMemcpyAsync(&h, ctrl, sizeof(DfsphCtrl), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(ctx, cudaStreamSynchronize(st));
-            batch = 2;  // the guess was short: continue in pairs
-        }
-    }
+    int rc = dfsph_solve_loop(ctx, mode, max_iterations, eta, offset, n_fluid, first_batch, &h, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
     if (iterations_out) *iterations_out = h.iterations;
     if (sweeps_out) *sweeps_out = h.sweeps;
     if (avg_err_out) *avg_err_out = h.last_avg;
+    return SPH_OK;
+}
+
+int sph_dfsph_step(SphCtx *ctx, int32_t nsteps, SphDfsphStep *io, void *stream) {
+    if (!ctx || !io || nsteps < 0 || io->n_fluid < 1) return SPH_E_ARG;
+    if (!ctx->P.dfsph) return fail(ctx, SPH_E_ARG, "sph_set_dfsph(1) was not called");
+    if (ctx->P.slab_on) return fail(ctx, SPH_E_ARG, "DFSPH is single-GPU");
+    if (ctx->P.n == 0) return SPH_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int s = 0; s < nsteps; ++s) {
+        // ps.initialize_particle_system(), compute_moving_boundary_volume() (sph_base.py:264-265)
+        int rc = launch_neighbor_build(ctx, st, nullptr, &ctx->launches);
+        if (rc) return rc;
+        if (ctx->has_dynamic_solids) { rc = launch_boundary_volume(ctx, 1, st, &ctx->launches); if (rc) return rc; }
+        const DevParams &P = ctx->P;  // after the build: the array binding changed sides
+        const int b128 = blocks_for(P.n, 128), b256 = blocks_for(P.n, 256);
+        // substep (DFSPH.py:399-408)
+        launch_pair_density(ctx, st, &ctx->launches);
+        ctx->list_valid = true;
+        k_dfsph_factor<<<b128, 128, 0, st>>>(P, ctx->S);
+        ctx->launches += 1;
+        DfsphCtrl h{};
+        if (io->enable_divergence_solver) {  // divergence_solve, DFSPH.py:236-276
+            k_dfsph_density_change<0><<<b128, 128, 0, st>>>(P, ctx->S);
+            k_dfsph_multiply_factor<<<b256, 256, 0, st>>>(P, ctx->S, io->inv_dt);
+            ctx->launches += 2;
+            rc = dfsph_solve_loop(ctx, 0, io->max_iterations_v, io->eta_v, 0.0f, io->n_fluid, io->first_batch_v, &h, st);
+            if (rc) return rc;
+            io->iterations_v = h.iterations; io->avg_err_v = h.last_avg; io->first_batch_v = std::max(1, h.sweeps);
+            k_dfsph_multiply_factor<<<b256, 256, 0, st>>>(P, ctx->S, io->dt);
+            ctx->launches += 1;
+        }
+        k_dfsph_non_pressure<<<b128, 128, 0, st>>>(P, ctx->S);
+        k_dfsph_predict_velocity<<<b256, 256, 0, st>>>(P, ctx->S);
+        // pressure_solve, DFSPH.py:314-352
+        k_dfsph_density_change<1><<<b128, 128, 0, st>>>(P, ctx->S);
+        k_dfsph_multiply_factor<<<b256, 256, 0, st>>>(P, ctx->S, io->inv_dt2);
+        ctx->launches += 4;
+        rc = dfsph_solve_loop(ctx, 1, io->max_iterations, io->eta, io->density0, io->n_fluid, io->first_batch, &h, st);
+        if (rc) return rc;
+        io->iterations = h.iterations; io->avg_err = h.last_avg; io->first_batch = std::max(1, h.sweeps);
+        k_dfsph_advect<<<b256, 256, 0, st>>>(P, ctx->S);
+        ctx->launches += 1;
+        ctx->built = false; ctx->list_valid = false;
+        // solve_rigid_body(), enforce_boundary_3D(fluid) (sph_base.py:270-271)
+        if (!ctx->bodies.empty()) { rc = launch_rigid_solve(ctx, st, &ctx->launches); if (rc) return rc; }
+        k_enforce_boundary<<<b256, 256, 0, st>>>(P, ctx->S, /*particle_type=*/1);
+        ctx->launches += 1;
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
     return SPH_OK;
 }
 

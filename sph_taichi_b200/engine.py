@@ -206,6 +206,10 @@ class Engine:
                                              self._stream()), "sph_dfsph_solve")
         return int(it.value), int(sw.value), float(avg.value)
 
+    def dfsph_step(self, nsteps, io):
+        """`nsteps` whole DFSPH steps launched from one call; `io` is a _lib.SphDfsphStep (constants in, counts out)."""
+        self._check(self.lib.sph_dfsph_step(self.ctx, int(nsteps), C.byref(io), self._stream()), "sph_dfsph_step")
+
     def step(self, nsteps=1):
         self._check(self.lib.sph_step(self.ctx, int(nsteps), self._stream()), "sph_step")
 

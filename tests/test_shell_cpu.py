@@ -158,6 +158,9 @@ def test_dfsph_host_loops(fake_engine):
     s.pressure_solve()
     assert [c for c in eng.log if c.startswith("dfsph_solve")] == ["dfsph_solve:1:3", "dfsph_solve:1:3"]
     assert s.last_iterations == 2
+    eng.log.clear()
+    s.step(3)  # the whole step is one library call in this mode
+    assert [c for c in eng.log if "dfsph" in c] == ["dfsph_step"]
     # the reference's own loop structure: one density-error read-back per sweep
     s.device_side_loops = False
     eng.log.clear()
