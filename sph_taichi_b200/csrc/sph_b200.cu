@@ -1067,8 +1067,8 @@ int sph_dfsph_op(SphCtx *ctx, int32_t op, float arg, void *out_dev, void *stream
             k_dfsph_density_error<<<b256, 256, 0, st>>>(P, ctx->S, arg, static_cast<double *>(out_dev));
             break;
         case DFSPH_MULTIPLY_FACTOR: k_dfsph_multiply_factor<<<b256, 256, 0, st>>>(P, ctx->S, arg); break;
-        case DFSPH_DIVERGENCE_ITERATION: k_dfsph_iteration<0, false><<<b128, 128, 0, st>>>(P, ctx->S, nullptr); break;
-        case DFSPH_PRESSURE_ITERATION: k_dfsph_iteration<1, false><<<b128, 128, 0, st>>>(P, ctx->S, nullptr); break;
+        case DFSPH_DIVERGENCE_ITERATION: k_dfsph_iteration<0><<<b128, 128, 0, st>>>(P, ctx->S, nullptr); break;
+        case DFSPH_PRESSURE_ITERATION: k_dfsph_iteration<1><<<b128, 128, 0, st>>>(P, ctx->S, nullptr); break;
         case DFSPH_NON_PRESSURE_FORCES: k_dfsph_non_pressure<<<b128, 128, 0, st>>>(P, ctx->S); break;
         case DFSPH_PREDICT_VELOCITY: k_dfsph_predict_velocity<<<b256, 256, 0, st>>>(P, ctx->S); break;
         case DFSPH_ADVECT:
@@ -1097,27 +1097,15 @@ int dfsph_solve_loop(SphCtx *ctx, int mode, int32_t max_iterations, double eta, 
     CUDA_TRY(ctx, cudaMemsetAsync(ctrl, 0, sizeof(DfsphCtrl), st));
     if (P.n == 0) return SPH_OK;
     const int b128 = blocks_for(P.n, 128);
-    // SPH_DFSPH_PACKED=0: the sweeps gather posm / aux / dfs / veld separately like the op-by-op kernels (A/B)
-    static const bool packed = !(std::getenv("SPH_DFSPH_PACKED") && std::atoi(std::getenv("SPH_DFSPH_PACKED")) == 0);
-    if (packed) {
-        k_dfsph_publish<<<blocks_for(P.n, 256), 256, 0, st>>>(P, ctx->S, mode == 0 ? 0.0f : 1.0f);
-        ctx->launches += 1;
-    }
     int batch = std::max(1, std::min(first_batch, 64));
     while (!h->done) {
         for (int s = 0; s < batch; ++s) {
-            if (mode == 0 && packed) {
-                k_dfsph_iteration<0, true><<<b128, 128, 0, st>>>(P, ctx->S, ctrl);
-                k_dfsph_density_change_err<0, true><<<b128, 128, 0, st>>>(P, ctx->S, offset, ctrl);
-            } else if (mode == 0) {
-                k_dfsph_iteration<0, false><<<b128, 128, 0, st>>>(P, ctx->S, ctrl);
-                k_dfsph_density_change_err<0, false><<<b128, 128, 0, st>>>(P, ctx->S, offset, ctrl);
-            } else if (packed) {
-                k_dfsph_iteration<1, true><<<b128, 128, 0, st>>>(P, ctx->S, ctrl);
-                k_dfsph_density_change_err<1, true><<<b128, 128, 0, st>>>(P, ctx->S, offset, ctrl);
+            if (mode == 0) {
+                k_dfsph_iteration<0><<<b128, 128, 0, st>>>(P, ctx->S, ctrl);
+                k_dfsph_density_change_err<0><<<b128, 128, 0, st>>>(P, ctx->S, offset, ctrl);
             } else {
-                k_dfsph_iteration<1, false><<<b128, 128, 0, st>>>(P, ctx->S, ctrl);
-                k_dfsph_density_change_err<1, false><<<b128, 128, 0, st>>>(P, ctx->S, offset, ctrl);
+                k_dfsph_iteration<1><<<b128, 128, 0, st>>>(P, ctx->S, ctrl);
+                k_dfsph_density_change_err<1><<<b128, 128, 0, st>>>(P, ctx->S, offset, ctrl);
             }
             k_dfsph_check<<<1, 1, 0, st>>>(ctrl, (double)n_fluid, eta, max_iterations);
         }

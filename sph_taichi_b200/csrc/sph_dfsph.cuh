@@ -36,48 +36,33 @@ struct DfsphCtrl {
 };
 
 // Dense walk over the neighbour list of particle i (reference visiting order), gathers batched by
-// four; falls back to the 27-cell scan when the list overflowed.  fn(j, rx, ry, rz, r2, posm_j, b_j).
-// PACKED: the neighbour comes as ONE 32-byte record {x, y, z, m_V | vx, vy, vz, k or tag} of S.fpv (k_dfsph_publish)
-// fetched with a single 256-bit load -- one sector per neighbour instead of one per gathered array; otherwise
-// b_j is not loaded and fn gathers what it needs.
-template <bool PACKED, typename F>
-__device__ __forceinline__ void for_listed_neighbors_b(const DevParams &P, const DevArrays &S, int i, const float4 &pi,
-                                                       F &&fn) {
+// four; falls back to the 27-cell scan when the list overflowed.  fn(j, rx, ry, rz, r2, posm_j).
+template <typename F>
+__device__ __forceinline__ void for_listed_neighbors(const DevParams &P, const DevArrays &S, int i, const float4 &pi,
+                                                     F &&fn) {
     const int cnt = S.nbr_cnt[i];
     if (cnt != NBR_OVERFLOW) {
         const int32_t *lp = S.nbr_list + i;
         const size_t stride = (size_t)S.npad;
         for (int k0 = 0; k0 < cnt; k0 += 4) {
             int j[4];
-            float4 pj[4], bj[4];
+            float4 pj[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 j[u] = (k0 + u < cnt) ? lp[(size_t)(k0 + u) * stride] : i;
-                if (PACKED) ldg256(S.fpv + 2 * (size_t)j[u], pj[u], bj[u]);
-                else { pj[u] = __ldg(S.posm + j[u]); bj[u] = pj[u]; }
+                pj[u] = __ldg(S.posm + j[u]);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (k0 + u < cnt) {
                     float rx = pi.x - pj[u].x, ry = pi.y - pj[u].y, rz = pi.z - pj[u].z;
-                    fn(j[u], rx, ry, rz, rx * rx + ry * ry + rz * rz, pj[u], bj[u]);
+                    fn(j[u], rx, ry, rz, rx * rx + ry * ry + rz * rz, pj[u]);
                 }
             }
         }
     } else {
-        for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z,
-                          [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
-                              float4 a = pj, b = pj;
-                              if (PACKED) ldg256(S.fpv + 2 * (size_t)j, a, b);
-                              fn(j, rx, ry, rz, r2, pj, b);
-                          });
+        for_all_neighbors(P, S.posm, S.cell_end, i, pi.x, pi.y, pi.z, fn);
     }
-}
-template <typename F>
-__device__ __forceinline__ void for_listed_neighbors(const DevParams &P, const DevArrays &S, int i, const float4 &pi,
-                                                     F &&fn) {
-    for_listed_neighbors_b<false>(P, S, i, pi, [&](int j, float rx, float ry, float rz, float r2, const float4 &pj,
-                                                   const float4 &) { fn(j, rx, ry, rz, r2, pj); });
 }
 
 __device__ __forceinline__ bool dfsph_fluid(const DevParams &P, const DevArrays &S, int i, uint32_t &fl) {
@@ -111,16 +96,14 @@ __global__ void __launch_bounds__(128) k_dfsph_factor(DevParams P, DevArrays S) 
 }
 
 // MODE 0: compute_density_change (DFSPH.py:157-196);  MODE 1: compute_density_adv (DFSPH.py:198-219)
-template <int MODE, bool PACKED>
+template <int MODE>
 __device__ __forceinline__ float dfsph_density_change_of(const DevParams &P, const DevArrays &S, int i) {
     float4 pi = S.posm[i];
     float4 vi = S.veld[i];
     float acc = 0.f;
     int nn = 0;
-    for_listed_neighbors_b<PACKED>(P, S, i, pi, [&](int j, float rx, float ry, float rz, float r2, const float4 &pj,
-                                                    const float4 &bj) {
-        float4 vj = bj;
-        if (!PACKED) vj = __ldg(S.veld + j);
+    for_listed_neighbors(P, S, i, pi, [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
+        float4 vj = __ldg(S.veld + j);
         float gs = gradw_of(P, r2);
         acc += pj.w * (((vi.x - vj.x) * rx + (vi.y - vj.y) * ry + (vi.z - vj.z) * rz) * gs);
         ++nn;
@@ -133,8 +116,6 @@ __device__ __forceinline__ float dfsph_density_change_of(const DevParams &P, con
         da = fmaxf(vi.w / P.rho0 + P.dt * acc, 1.0f);
     }
     S.dfs[i].y = da;
-    if (PACKED)  // this sweep's kappa of particle i for the next iteration kernel (see k_dfsph_publish)
-        reinterpret_cast<float *>(S.fpv + 2 * (size_t)i + 1)[3] = __fmul_rn(da - (MODE == 0 ? 0.0f : 1.0f), S.dfs[i].x);
     return da;
 }
 template <int MODE>
@@ -142,7 +123,7 @@ __global__ void __launch_bounds__(128) k_dfsph_density_change(DevParams P, DevAr
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t fl;
     if (!dfsph_fluid(P, S, i, fl)) return;
-    dfsph_density_change_of<MODE, false>(P, S, i);
+    dfsph_density_change_of<MODE>(P, S, i);
 }
 
 // block-wide fp64 sum -> one atomic per CTA (DFSPH.py:221-227 returns the sum to the host)
@@ -163,34 +144,14 @@ __device__ __forceinline__ void dfsph_block_sum_to(double e, double *out) {
 
 // One sweep of sph_dfsph_solve = k_dfsph_iteration + this kernel + k_dfsph_check: the density change / advected
 // density of the sweep and its error sum in ONE pass (the host loop runs compute_density_error as a second kernel).
-template <int MODE, bool PACKED>
+template <int MODE>
 __global__ void __launch_bounds__(128) k_dfsph_density_change_err(DevParams P, DevArrays S, float offset, DfsphCtrl *ctrl) {
     if (ctrl->done) return;  // written only by k_dfsph_check, between kernels: uniform over the grid
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t fl;
     double e = 0.0;
-    if (dfsph_fluid(P, S, i, fl)) e = (double)(P.rho0 * dfsph_density_change_of<MODE, PACKED>(P, S, i) - offset);
+    if (dfsph_fluid(P, S, i, fl)) e = (double)(P.rho0 * dfsph_density_change_of<MODE>(P, S, i) - offset);
     dfsph_block_sum_to<4>(e, &ctrl->err);
-}
-
-// The packed records the sweeps of sph_dfsph_solve gather: {x, y, z, m_V | vx, vy, vz, kappa} per particle in S.fpv
-// (free in DFSPH mode), kappa = (density_adv - boff) * dfsph_factor for a fluid particle, +inf / -inf for a static /
-// dynamic boundary particle.  Written once before the loop; inside the loop the iteration kernel refreshes the
-// velocity of its particle and the density-change kernel its kappa.
-__global__ void k_dfsph_publish(DevParams P, DevArrays S, float boff) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
-    const float inf = __int_as_float(0x7f800000);
-    float4 p = S.posm[i], v = S.veld[i];
-    const uint32_t fl = __float_as_uint(S.misc[i].z);
-    if (fl & FLAG_FLUID) {
-        float4 d = S.dfs[i];
-        v.w = __fmul_rn(d.y - boff, d.x);
-    } else {
-        v.w = (fl & FLAG_DYNAMIC) ? -inf : inf;
-    }
-    S.fpv[2 * (size_t)i] = p;
-    S.fpv[2 * (size_t)i + 1] = v;
 }
 
 // The loop condition of divergence_solve / pressure_solve (DFSPH.py:245-254, 323-331), evaluated on the device:
@@ -227,7 +188,7 @@ __global__ void k_dfsph_multiply_factor(DevParams P, DevArrays S, float ts) {
 // MODE 0: divergence_solver_iteration_kernel (DFSPH.py:278-311);  MODE 1: pressure_solve_iteration_kernel
 // (DFSPH.py:354-389).  The reactions MODE 0 would add to dynamic rigid particles are overwritten by
 // compute_non_pressure_forces before anything reads them (DFSPH.py:402), so only MODE 1 scatters them.
-template <int MODE, bool PACKED>
+template <int MODE>
 __global__ void __launch_bounds__(128) k_dfsph_iteration(DevParams P, DevArrays S, const DfsphCtrl *ctrl) {
     if (ctrl && ctrl->done) return;  // sph_dfsph_solve: a sweep launched behind the converged one
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -235,33 +196,16 @@ __global__ void __launch_bounds__(128) k_dfsph_iteration(DevParams P, DevArrays 
     if (!dfsph_fluid(P, S, i, fl)) return;
     const float eps = 1e-5f;
     const float boff = MODE == 0 ? 0.0f : 1.0f;
-    const float inf = __int_as_float(0x7f800000);
     float4 pi = S.posm[i];
     float4 vi = S.veld[i];
     float4 di = S.dfs[i];
-    // kappa_i + kappa_j without FMA contraction: the packed sweeps read kappa_j ready-made, the op-by-op kernels
-    // form it here -- same bits either way (and the same two roundings as the CPU oracle)
-    const float k_i = __fmul_rn(di.y - boff, di.x);
+    const float k_i = (di.y - boff) * di.x;
     float dvx = 0.f, dvy = 0.f, dvz = 0.f;
-    for_listed_neighbors_b<PACKED>(P, S, i, pi, [&](int j, float rx, float ry, float rz, float r2, const float4 &pj,
-                                                    const float4 &bj) {
-        bool fluid_j, dynamic_j;
-        float k_j = bj.w, body_density = 0.0f;
-        if (PACKED) {
-            fluid_j = fabsf(k_j) != inf;
-            dynamic_j = k_j < 0.0f;
-        } else {
-            float4 aj = __ldg(S.aux + j);
-            fluid_j = aj.z > 0.0f;
-            dynamic_j = aj.z < -1.5f;
-            body_density = aj.x;
-            if (fluid_j) {
-                float4 dj = __ldg(S.dfs + j);
-                k_j = __fmul_rn(dj.y - boff, dj.x);
-            }
-        }
-        if (fluid_j) {
-            float k_sum = __fadd_rn(k_i, k_j);
+    for_listed_neighbors(P, S, i, pi, [&](int j, float rx, float ry, float rz, float r2, const float4 &pj) {
+        float4 aj = __ldg(S.aux + j);
+        if (aj.z > 0.0f) {  // fluid neighbour
+            float4 dj = __ldg(S.dfs + j);
+            float k_sum = k_i + (dj.y - boff) * dj.x;
             if (fabsf(k_sum) > eps) {
                 float s = -pj.w * gradw_of(P, r2);  // grad_p_j = s * r
                 float c = P.dt * k_sum * s;
@@ -274,9 +218,8 @@ __global__ void __launch_bounds__(128) k_dfsph_iteration(DevParams P, DevArrays 
             if (MODE == 0) { dvx += c * rx; dvy += c * ry; dvz += c * rz; }
             else {
                 vi.x += c * rx; vi.y += c * ry; vi.z += c * rz;
-                if (dynamic_j) {  // dynamic rigid body: reaction, DFSPH.py:388-389
-                    if (PACKED) body_density = __ldg(&S.aux[j].x);
-                    float f = -(1.0f / P.dt) * vi.w / body_density;
+                if (aj.z < -1.5f) {  // dynamic rigid body: reaction, DFSPH.py:388-389
+                    float f = -(1.0f / P.dt) * vi.w / aj.x;
                     float *a = reinterpret_cast<float *>(S.acc + j);
                     atomicAdd(a + 0, c * rx * f);
                     atomicAdd(a + 1, c * ry * f);
@@ -287,7 +230,6 @@ __global__ void __launch_bounds__(128) k_dfsph_iteration(DevParams P, DevArrays 
     });
     if (MODE == 0) { vi.x += dvx; vi.y += dvy; vi.z += dvz; }
     S.veld[i] = vi;
-    if (PACKED) S.fpv[2 * (size_t)i + 1] = make_float4(vi.x, vi.y, vi.z, k_i);  // new velocity, same kappa
 }
 
 // compute_non_pressure_forces (DFSPH.py:50-101): cohesion + viscosity, list based
