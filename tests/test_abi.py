@@ -80,3 +80,28 @@ def test_capacity_limit_is_reported_before_any_device_work():
     rc = lib.sph_create(ctypes.byref(p), bad_n, 0, 0, 0, None, 0, ctypes.byref(h))
     assert rc < 0 and b"32-bit" in lib.sph_last_error(None), lib.sph_last_error(None)
     assert not h.value
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """Every struct that crosses the ABI: size and field offsets of the ctypes mirror in _lib.py equal what a C
+    compiler makes of include/sph_b200.h (a silent mismatch would scramble parameters, not fail)."""
+    import subprocess
+    from sph_taichi_b200 import _lib
+    structs = ["SphParams", "SphFields", "SphRigidBody", "SphTransport", "SphDfsphStep"]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sph_b200.h"', "int main(void) {"]
+    for sn in structs:
+        st = getattr(_lib, sn)
+        lines.append(f'  printf("{sn} %zu\\n", sizeof({sn}));')
+        for fn, *_ in st._fields_:
+            lines.append(f'  printf("{sn}.{fn} %zu\\n", offsetof({sn}, {fn}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for sn in structs:
+        st = getattr(_lib, sn)
+        assert ctypes.sizeof(st) == int(out[sn]), sn
+        for fn, *_ in st._fields_:
+            assert getattr(st, fn).offset == int(out[f"{sn}.{fn}"]), f"{sn}.{fn}"
