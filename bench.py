@@ -208,7 +208,7 @@ class ClockSampler:
 
 def best_thread_count(o, reps=3):
     """Give the CPU arm its best shot: the pair loops are memory-latency bound and SMT siblings can hurt, so
-    time `reps` steps (after one untimed step) at cpu_count, /2, /4 and /8 threads (plus the cgroup CPU quota when the
+    time `reps` steps (after one step) at cpu_count / 8, / 4, / 2 and cpu_count threads (plus the cgroup CPU quota when the
     box has one -- on this pool 128 threads run at 0.7 steps/s against 14 at 16-32, the signature of a quota well
     below the visible thread count, see profiles/r02_cpu_arm_binding.txt) and keep the fastest.  Returns
     (best, {threads: steps/s}) -- round 1 timed ONE step per candidate and picked 32 threads on one box and 64 on
@@ -220,13 +220,24 @@ def best_thread_count(o, reps=3):
     quota = cgroup_cpu_quota()
     if quota:
         cand.add(max(1, min(total, int(quota))))
-    for n in sorted(cand, reverse=True):
+    # ascending, and stop at the first count whose FIRST step is already twice as slow as the best so far: past the
+    # cores the box really schedules, more threads only get worse (128 threads: 0.7 steps/s against 14 at 16-32 on
+    # this pool), and on the 16 M-particle scene of the 8-GPU reference arm one such step costs a minute
+    best_step = None
+    for n in sorted(cand):
         set_threads(n)
+        t0 = time.perf_counter()
         o.step()
+        first = time.perf_counter() - t0
+        if best_step is not None and first > 2.0 * best_step:
+            table[n] = 1.0 / first
+            break
         t0 = time.perf_counter()
         for _ in range(reps):
             o.step()
-        table[n] = reps / (time.perf_counter() - t0)
+        per = (time.perf_counter() - t0) / reps
+        table[n] = 1.0 / per
+        best_step = per if best_step is None else min(best_step, per)
     best = max(table, key=table.get)
     set_threads(best)
     return best, table
